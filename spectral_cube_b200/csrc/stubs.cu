@@ -1,0 +1,37 @@
+// stubs.cu -- entry points declared in include/sc_b200.h whose kernels are not written yet.
+// They fail loudly (SC_ERR_UNSUPPORTED); nothing falls back to the CPU.
+#include "common.cuh"
+
+#define SC_STUB(name) \
+    scb::set_error(name " is not implemented yet in this build of libsc_b200"); return SC_ERR_UNSUPPORTED;
+
+extern "C" {
+
+int sc_moments_spatial(const float *, int64_t, int64_t, int64_t, int64_t, int64_t, int,
+                       const sc_mask_desc *, const double *, double, int, double *, double *, double *, void *) { SC_STUB("sc_moments_spatial") }
+
+int sc_spectral_smooth(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                       const sc_mask_desc *, double, const double *, int, int, void *, size_t, void *) { SC_STUB("sc_spectral_smooth") }
+
+int sc_smooth_moments_axis0(const float *, int64_t, int64_t, int64_t, int64_t, int64_t, const sc_mask_desc *, double,
+                            const double *, int, int, const double *, double, double, int, double *, double *, double *,
+                            void *, size_t, void *) { SC_STUB("sc_smooth_moments_axis0") }
+
+int sc_spatial_smooth_sep(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                          const sc_mask_desc *, double, const double *, int, const double *, int,
+                          const float *, const float *, int, int, void *, size_t, void *) { SC_STUB("sc_spatial_smooth_sep") }
+
+int sc_spatial_smooth_2d(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                         const sc_mask_desc *, double, const double *, int, int,
+                         const float *, const float *, int, int, void *, size_t, void *) { SC_STUB("sc_spatial_smooth_2d") }
+
+int sc_spectral_interp(const float *, void *, int, uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                       const sc_mask_desc *, double, const double *, const double *, int, double, int, int, int,
+                       void *, size_t, void *) { SC_STUB("sc_spectral_interp") }
+
+int sc_reproject(const float *, void *, int, uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                 const sc_mask_desc *, double, const double *, const double *, int, void *) { SC_STUB("sc_reproject") }
+
+int sc_wcs_pixel_map(const double *, const double *, int64_t, int64_t, double *, double *, void *) { SC_STUB("sc_wcs_pixel_map") }
+
+}

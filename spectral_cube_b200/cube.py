@@ -1,0 +1,426 @@
+"""
+``SpectralCube`` / ``DaskSpectralCube`` with the reference's method surface for the hot path
+(spectral_cube/spectral_cube.py, spectral_cube/dask_spectral_cube.py), backed by
+libsc_b200 (hand-written CUDA for sm_100a, called through the C ABI in include/sc_b200.h).
+
+The cube's float32 voxels live in HBM (a torch tensor is used purely as the memory holder);
+masks are lazy expression trees evaluated inside the kernels; host work per call is
+O(nchan).  Where the two reference classes differ (output dtype of smoothing, behaviour
+outside the input range when interpolating, meta keys) ``SpectralCube`` mirrors the numpy
+class and ``DaskSpectralCube`` the dask class.  Nothing here falls back to the CPU.
+"""
+import operator
+import warnings
+
+import numpy as np
+
+from . import _lib
+from . import masks as _masks
+from .masks import (BooleanArrayMask, LazyMask, LazyComparisonMask, MaskBase, lower_mask)
+from .projection import Projection, _unit_mul, _unit_pow
+from .wcs import as_cube_wcs, spectral_unit_scale
+
+SIGMA2FWHM = 2. * np.sqrt(2. * np.log(2.))        # spectral_cube.py:82
+MEMORY_THRESHOLD = 1e8                            # cube_utils.py:266-268
+
+
+class SpectralCubeWarning(Warning):
+    pass
+
+
+class VarianceWarning(SpectralCubeWarning):      # utils.py
+    pass
+
+
+class SmoothingWarning(SpectralCubeWarning):
+    pass
+
+
+class BeamUnitsError(Exception):
+    pass
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def _stream():
+    return _torch().cuda.current_stream().cuda_stream
+
+
+class BaseSpectralCube(object):
+    _mirrors_dask = False
+
+    def __init__(self, data, wcs, mask=None, meta=None, fill_value=np.nan, header=None,
+                 allow_huge_operations=False, unit=None, spectral_unit=None, device=None, **kwargs):
+        torch = _torch()
+        if isinstance(data, torch.Tensor):
+            t = data
+            if t.dtype != torch.float32:
+                t = t.to(torch.float32)
+            if not t.is_cuda:
+                t = t.cuda(device)
+        else:
+            arr = np.asarray(data)
+            if arr.ndim != 3:
+                raise ValueError("data should be a 3-d array")
+            t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).cuda(device)
+        if t.dim() != 3:
+            raise ValueError("data should be a 3-d array")
+        if t.stride(2) != 1:
+            t = t.contiguous()
+        self._data = t
+        self._wcs = as_cube_wcs(wcs)
+        if mask is not None and not isinstance(mask, MaskBase):
+            mask = BooleanArrayMask(np.asarray(mask, dtype=bool), self._wcs, shape=tuple(t.shape))
+        self._mask = mask
+        self._meta = dict(meta or {})
+        self._header = dict(header or {})
+        if unit is None:
+            unit = self._meta.get('BUNIT', self._header.get('BUNIT', ''))
+        self._unit = unit
+        self._fill_value = fill_value
+        self.allow_huge_operations = allow_huge_operations
+        self._spectral_unit = spectral_unit if spectral_unit is not None else self._wcs.cunit[2]
+        self._spectral_scale = spectral_unit_scale(self._wcs.cunit[2], self._spectral_unit)
+        self._workspace = None
+        self._pending = None            # lazy op recorded by DaskSpectralCube (see spectral_smooth)
+
+    # -- construction ------------------------------------------------------------------------
+    def _new_cube_with(self, data=None, wcs=None, mask=None, meta=None, fill_value=None,
+                       spectral_unit=None, unit=None, cls=None, **kw):
+        """spectral_cube.py:244-289"""
+        cls = cls or type(self)
+        cube = cls.__new__(cls)
+        BaseSpectralCube.__init__(
+            cube,
+            data=self._data if data is None else data,
+            wcs=self._wcs if wcs is None else wcs,
+            mask=self._mask if mask is None else mask,
+            meta=self._meta if meta is None else meta,
+            fill_value=self._fill_value if fill_value is None else fill_value,
+            header=self._header, allow_huge_operations=self.allow_huge_operations,
+            unit=self._unit if unit is None else unit,
+            spectral_unit=self._spectral_unit if spectral_unit is None else spectral_unit)
+        return cube
+
+    # -- basic properties ------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return tuple(self._data.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def ndim(self):
+        return 3
+
+    @property
+    def unit(self):
+        return self._unit
+
+    @property
+    def wcs(self):
+        return self._wcs
+
+    @property
+    def mask(self):
+        return self._mask
+
+    @property
+    def meta(self):
+        return self._meta
+
+    @property
+    def fill_value(self):
+        return self._fill_value
+
+    @property
+    def header(self):
+        hdr = dict(self._header)
+        hdr.update(self._wcs.to_header())
+        hdr['BUNIT'] = str(self._unit)
+        hdr['NAXIS'] = 3
+        hdr['NAXIS1'], hdr['NAXIS2'], hdr['NAXIS3'] = self.shape[2], self.shape[1], self.shape[0]
+        return hdr
+
+    @property
+    def spectral_axis(self):
+        """Channel centres in the cube's spectral unit (spectral_cube.py:1765-1771)."""
+        return self._wcs.spectral_pix2world(np.arange(self.shape[0])) * self._spectral_scale
+
+    @property
+    def device_data(self):
+        """The float32 device tensor holding the voxels (memory holder only)."""
+        return self._data
+
+    def with_mask(self, mask, inherit_mask=True, wcs_tolerance=None):
+        """spectral_cube.py:1259-1306"""
+        if isinstance(mask, np.ndarray):
+            if not _masks.is_broadcastable_and_smaller(self.shape, mask.shape):
+                raise ValueError("Mask shape is not broadcastable to data shape: "
+                                 "%s vs %s" % (mask.shape, self.shape))
+            mask = BooleanArrayMask(mask, self._wcs, shape=self.shape)
+        if self._mask is not None and inherit_mask:
+            new_mask = self._mask & mask
+        else:
+            new_mask = mask
+        cube = self._new_cube_with()
+        cube._mask = new_mask
+        return cube
+
+    def with_fill_value(self, fill_value):
+        return self._new_cube_with(fill_value=fill_value)
+
+    def with_spectral_unit(self, unit, **kwargs):
+        return self._new_cube_with(spectral_unit=unit)
+
+    # -- comparison operators -> lazy masks (spectral_cube.py:2263-2296) ---------------------------
+    def _val_to_own_unit(self, value):
+        if hasattr(value, 'unit') and hasattr(value, 'to') and not isinstance(self._unit, str):
+            return value.to(self._unit).value
+        if hasattr(value, 'value') and hasattr(value, 'unit'):
+            return value.value
+        return value
+
+    def _cmp(self, op, value):
+        value = self._val_to_own_unit(value)
+        return LazyComparisonMask(op, value, data=self._data, wcs=self._wcs)
+
+    def __gt__(self, value):
+        return self._cmp(operator.gt, value)
+
+    def __ge__(self, value):
+        return self._cmp(operator.ge, value)
+
+    def __lt__(self, value):
+        return self._cmp(operator.lt, value)
+
+    def __le__(self, value):
+        return self._cmp(operator.le, value)
+
+    def __eq__(self, value):
+        return self._cmp(operator.eq, value)
+
+    def __ne__(self, value):
+        return self._cmp(operator.ne, value)
+
+    def __hash__(self):
+        return id(self)
+
+    # -- masked data access (base_class.py:389-450) ------------------------------------------------
+    def _mask_desc(self):
+        return lower_mask(self._mask, self._data)
+
+    def _filled_tensor(self, fill=np.nan):
+        torch = _torch()
+        lib = _lib.load()
+        if self._mask is None:
+            return self._data
+        desc, keep = self._mask_desc()
+        out = torch.empty(self.shape, dtype=torch.float32, device=self._data.device)
+        nchan, ny, nx = self.shape
+        _lib.check(lib.sc_fill_masked(self._data.data_ptr(), nchan, ny, nx, self._data.stride(0),
+                                      self._data.stride(1), desc, float(fill), out.data_ptr(), _stream()))
+        return out
+
+    def _get_filled_data(self, view=(), fill=np.nan, **kwargs):
+        return self._filled_tensor(fill).cpu().numpy()[view]
+
+    @property
+    def filled_data(self):
+        return _Sliceable(lambda view: self._get_filled_data(view=view, fill=self._fill_value))
+
+    @property
+    def unitless_filled_data(self):
+        return self.filled_data
+
+    @property
+    def unmasked_data(self):
+        return _Sliceable(lambda view: self._data.cpu().numpy()[view])
+
+    def flattened(self, slice=(), weights=None):
+        return self._mask._flattened(self._data, view=slice) if self._mask is not None \
+            else self._data.cpu().numpy()[slice].ravel()
+
+    # -- coordinates (O(nchan) on the host) ----------------------------------------------------------
+    def _spectral_offsets(self):
+        """``_pix_cen()[0]`` reduced to its nchan-long content (spectral_cube.py:1473-1475)."""
+        spectral = self.spectral_axis.copy()
+        spectral -= spectral[0]
+        return spectral
+
+    def _pix_size_slice(self, axis):
+        """spectral_cube.py:1510-1535"""
+        psm = self._wcs.pixel_scale_matrix
+        if axis == 0:
+            return np.abs(psm[2, 2]) * self._spectral_scale
+        elif axis in (1, 2):
+            return np.sum(psm[2 - axis, :] ** 2) ** 0.5
+        raise ValueError("Cubes have 3 axes.")
+
+    def _world0_spectral(self):
+        """Spectral part of ``self.world[0, :, :]`` -- a constant (base_class.py:236-239)."""
+        return float(self._wcs.spectral_pix2world(0.0)) * self._spectral_scale
+
+    def _get_workspace(self, nbytes):
+        torch = _torch()
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self._data.device)
+        return self._workspace
+
+    # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
+    def _moments_axis0_raw(self, want_bits):
+        """Run the fused kernel; returns dict order -> float64 device tensor (ny, nx), with units
+        folded in the way ``moment()`` does (M1 already carries the channel-0 world offset)."""
+        torch = _torch()
+        lib = _lib.load()
+        if self._pending is not None:
+            return self._pending.moments(self, want_bits)
+        nchan, ny, nx = self.shape
+        dev = self._data.device
+        outs = {}
+        ptrs = []
+        for bit, order in ((1, 0), (2, 1), (4, 2)):
+            if want_bits & bit:
+                outs[order] = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+                ptrs.append(outs[order].data_ptr())
+            else:
+                ptrs.append(None)
+        desc, keep = self._mask_desc()
+        wsb = lib.sc_workspace_bytes(_lib.OP_MOMENTS, nchan, ny, nx, 0)
+        ws = self._get_workspace(wsb)
+        xoff, xptr = _lib.as_double_array(self._spectral_offsets())
+        _lib.check(lib.sc_moments_axis0(
+            self._data.data_ptr(), nchan, ny, nx, self._data.stride(0), self._data.stride(1), desc,
+            xptr, float(self._pix_size_slice(0)), self._world0_spectral(), want_bits,
+            ptrs[0], ptrs[1], ptrs[2], ws.data_ptr(), ws.numel(), _stream()))
+        return outs
+
+    def _moment_unit(self, order, axis):
+        axunit = self._spectral_unit if axis == 0 else 'deg'
+        if order == 0:
+            return _unit_mul(self._unit, axunit)
+        return _unit_pow(axunit, max(order, 1))
+
+    def _moment_meta(self, order, axis, how):
+        meta = {'moment_order': order, 'moment_axis': axis}
+        if not self._mirrors_dask:
+            meta['moment_method'] = how                 # spectral_cube.py:1714-1716 vs dask:1127-1128
+        meta.update(self._meta)
+        return meta
+
+    def moment(self, order=0, axis=0, how='auto', **kwargs):
+        if axis == 0 and order == 2:
+            warnings.warn("Note that the second moment returned will be a "
+                          "variance map. To get a linewidth map, use the "
+                          "SpectralCube.linewidth_fwhm() or "
+                          "SpectralCube.linewidth_sigma() methods instead.",
+                          VarianceWarning)
+        if not self._mirrors_dask and how not in ('slice', 'cube', 'ray', 'auto'):
+            # the reference *returns* the exception object (spectral_cube.py:1687-1689)
+            return ValueError("Invalid how. Must be in %s" % sorted(['slice', 'cube', 'ray', 'auto']))
+        if axis == 0:
+            out = self._moment_axis0(order)
+        else:
+            out = self._moment_spatial(order, axis)
+        return Projection(out, unit=self._moment_unit(order, axis), wcs=self._wcs.drop_axis(axis),
+                          meta=self._moment_meta(order, axis, how), header=self._header, copy=False)
+
+    def _moment_axis0(self, order):
+        torch = _torch()
+        lib = _lib.load()
+        if order in (0, 1, 2):
+            return self._moments_axis0_raw(1 << order)[order].cpu().numpy()
+        # higher orders: first moment pass, then a central-moment pass (_moments.py:108-123)
+        nchan, ny, nx = self.shape
+        m1 = self._moments_axis0_raw(_lib.WANT_M1)[1]
+        centre = m1 - self._world0_spectral()
+        out = torch.empty((ny, nx), dtype=torch.float64, device=self._data.device)
+        desc, keep = self._mask_desc()
+        ws = self._get_workspace(nchan * 8 + 512)
+        xoff, xptr = _lib.as_double_array(self._spectral_offsets())
+        src = self._materialized()
+        _lib.check(lib.sc_moment_central_axis0(
+            src._data.data_ptr(), nchan, ny, nx, src._data.stride(0), src._data.stride(1), desc,
+            xptr, centre.data_ptr(), int(order), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return out.cpu().numpy()
+
+    def _moment_spatial(self, order, axis):
+        raise NotImplementedError("moments along spatial axes are not built yet in this round")
+
+    def _materialized(self):
+        return self
+
+    def moment0(self, axis=0, how='auto', **kwargs):
+        return self.moment(axis=axis, order=0, how=how, **kwargs)
+
+    def moment1(self, axis=0, how='auto', **kwargs):
+        return self.moment(axis=axis, order=1, how=how, **kwargs)
+
+    def moment2(self, axis=0, how='auto', **kwargs):
+        return self.moment(axis=axis, order=2, how=how, **kwargs)
+
+    def moments012(self, how='auto'):
+        """Extension: moment 0, 1 and 2 from ONE pass over the cube (the reference needs four)."""
+        raw = self._moments_axis0_raw(7)
+        return tuple(Projection(raw[o].cpu().numpy(), unit=self._moment_unit(o, 0),
+                                wcs=self._wcs.drop_axis(0), meta=self._moment_meta(o, 0, how),
+                                header=self._header, copy=False) for o in (0, 1, 2))
+
+    def linewidth_sigma(self, how='auto', **kwargs):
+        with np.errstate(invalid='ignore'):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", VarianceWarning)
+                return self.moment2(how=how, **kwargs).sqrt()
+
+    def linewidth_fwhm(self, how='auto', **kwargs):
+        s = self.linewidth_sigma(**kwargs)               # the reference drops `how` here (:1763)
+        return s._with(s.value * SIGMA2FWHM, s.unit)
+
+
+class _Sliceable(object):
+    def __init__(self, getter):
+        self._getter = getter
+
+    def __getitem__(self, view):
+        return self._getter(view)
+
+
+class SpectralCube(BaseSpectralCube):
+    """Mirrors the numpy-backed reference class (spectral_cube.py:3691-3765).
+    ``SpectralCube(..., use_dask=True)`` returns a ``DaskSpectralCube`` (:3697-3702)."""
+
+    def __new__(cls, *args, **kwargs):
+        if kwargs.pop('use_dask', False) and cls is SpectralCube:
+            return super(SpectralCube, cls).__new__(DaskSpectralCube)
+        return super(SpectralCube, cls).__new__(cls)
+
+    def __init__(self, data, wcs, mask=None, meta=None, fill_value=np.nan, header=None,
+                 allow_huge_operations=False, beam=None, wcs_tolerance=0.0, use_dask=False, **kwargs):
+        super(SpectralCube, self).__init__(data=data, wcs=wcs, mask=mask, meta=meta,
+                                           fill_value=fill_value, header=header,
+                                           allow_huge_operations=allow_huge_operations, **kwargs)
+
+
+class DaskSpectralCube(SpectralCube):
+    """Mirrors the dask-backed reference class (dask_spectral_cube.py:1376-1650)."""
+    _mirrors_dask = True
+
+    def use_dask_scheduler(self, scheduler, num_workers=None):
+        """Accepted for drop-in compatibility (dask_spectral_cube.py:278-312); scheduling is the
+        GPU's business here."""
+        return _NullContext()
+
+    def rechunk(self, *args, **kwargs):
+        return self
+
+
+class _NullContext(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

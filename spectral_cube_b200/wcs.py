@@ -1,0 +1,184 @@
+"""
+Host-side coordinate metadata for the hot path.
+
+The reference leans on ``astropy.wcs`` (``base_class.py:178-241``, ``spectral_cube.py:1455-1535``).
+astropy is not a dependency of this package; what the hot path needs from a WCS is small and
+O(nchan): the spectral world value of every channel, the pixel scale matrix, and -- for
+``reproject`` -- the celestial parameters that the device-side pixel map
+(``sc_wcs_pixel_map``) consumes.  ``CubeWCS`` holds exactly that, in FITS conventions
+(1-based CRPIX, FITS axis order lon/lat/spectral), with wcslib's unit normalisation
+(celestial -> deg, spectral -> SI).  ``CubeWCS.from_astropy`` adapts a real
+``astropy.wcs.WCS`` when astropy is present.
+"""
+import copy as _copy
+
+import numpy as np
+
+_SI = {'m/s': ('m/s', 1.0), 'km/s': ('m/s', 1.0e3), 'cm/s': ('m/s', 1.0e-2),
+       'Hz': ('Hz', 1.0), 'kHz': ('Hz', 1.0e3), 'MHz': ('Hz', 1.0e6), 'GHz': ('Hz', 1.0e9),
+       'm': ('m', 1.0), 'cm': ('m', 1.0e-2), 'mm': ('m', 1.0e-3), 'um': ('m', 1.0e-6),
+       'nm': ('m', 1.0e-9), 'Angstrom': ('m', 1.0e-10), '': ('', 1.0)}
+_DEG = {'deg': 1.0, 'arcmin': 1.0 / 60.0, 'arcsec': 1.0 / 3600.0, 'rad': 180.0 / np.pi, '': 1.0}
+
+
+def spectral_unit_scale(si_unit, unit):
+    """Factor taking a value in the WCS's SI unit to ``unit`` (spectral_axis.py:67-73)."""
+    unit = str(unit)
+    if unit not in _SI or _SI[unit][0] != si_unit:
+        raise ValueError("unit %r is not convertible from %r" % (unit, si_unit))
+    return 1.0 / _SI[unit][1]
+
+
+class CubeWCS(object):
+    def __init__(self, ctype, crval, crpix, cdelt, cunit=('deg', 'deg', 'm/s'), pc=None, lonpole=None):
+        self.ctype = [str(c) for c in ctype]
+        crval = np.array(crval, dtype=np.float64)
+        cdelt = np.array(cdelt, dtype=np.float64)
+        cunit = [str(c) for c in cunit]
+        for i in (0, 1):
+            f = _DEG[cunit[i]]
+            crval[i] *= f
+            cdelt[i] *= f
+            cunit[i] = 'deg'
+        name, f = _SI[cunit[2]]
+        crval[2] *= f
+        cdelt[2] *= f
+        cunit[2] = name
+        self.crval, self.cdelt, self.cunit = crval, cdelt, cunit
+        self.crpix = np.array(crpix, dtype=np.float64)
+        self.pc = np.eye(3) if pc is None else np.array(pc, dtype=np.float64)
+        proj = self.ctype[0][-3:]
+        if proj not in ('TAN', 'SIN'):
+            raise NotImplementedError("celestial projection %r (TAN and SIN are supported)" % proj)
+        self.proj = proj
+        if lonpole is None:
+            lonpole = 0.0 if self.crval[1] >= 90.0 else 180.0        # FITS paper II, zenithal default
+        self.lonpole = float(lonpole)
+
+    # -- construction helpers -----------------------------------------------------------------
+    @classmethod
+    def from_header(cls, hdr):
+        """Build from a FITS-header-like mapping (CTYPEn, CRVALn, CRPIXn, CDELTn, CUNITn, PCi_j / CDi_j)."""
+        g = hdr.get
+        ctype = [g('CTYPE%d' % i) for i in (1, 2, 3)]
+        crval = [g('CRVAL%d' % i, 0.0) for i in (1, 2, 3)]
+        crpix = [g('CRPIX%d' % i, 0.0) for i in (1, 2, 3)]
+        cunit = [g('CUNIT%d' % i, 'deg' if i < 3 else '') for i in (1, 2, 3)]
+        if any(('CD%d_%d' % (i, j)) in hdr for i in (1, 2, 3) for j in (1, 2, 3)):
+            cd = np.array([[g('CD%d_%d' % (i, j), 0.0) for j in (1, 2, 3)] for i in (1, 2, 3)], dtype=np.float64)
+            cdelt = [1.0, 1.0, 1.0]
+            pc = cd
+        else:
+            cdelt = [g('CDELT%d' % i, 1.0) for i in (1, 2, 3)]
+            pc = np.array([[g('PC%d_%d' % (i, j), 1.0 if i == j else 0.0) for j in (1, 2, 3)]
+                           for i in (1, 2, 3)], dtype=np.float64)
+        return cls(ctype, crval, crpix, cdelt, cunit, pc=pc, lonpole=g('LONPOLE', None))
+
+    @classmethod
+    def from_astropy(cls, w):
+        ww = w.wcs
+        pc = ww.get_pc() if ww.has_pc() or not ww.has_cd() else ww.cd
+        cdelt = ww.cdelt if not ww.has_cd() else [1.0, 1.0, 1.0]
+        return cls(list(ww.ctype), list(ww.crval), list(ww.crpix), list(cdelt),
+                   [str(c) for c in ww.cunit], pc=np.array(pc), lonpole=float(ww.lonpole) if np.isfinite(ww.lonpole) else None)
+
+    def copy(self):
+        return _copy.deepcopy(self)
+
+    # -- what the hot path needs ----------------------------------------------------------------
+    @property
+    def pixel_scale_matrix(self):
+        return self.cdelt[:, None] * self.pc
+
+    def spectral_pix2world(self, pz):
+        """SI world value of 0-based spectral pixel(s) ``pz`` (linear axis)."""
+        pz = np.asarray(pz, dtype=np.float64)
+        return self.crval[2] + self.cdelt[2] * self.pc[2, 2] * (pz + 1.0 - self.crpix[2])
+
+    def celestial_params(self):
+        """The 12 doubles ``sc_wcs_pixel_map`` takes."""
+        m = self.pixel_scale_matrix
+        return np.array([self.crpix[0], self.crpix[1], self.crval[0], self.crval[1],
+                         m[0, 0], m[0, 1], m[1, 0], m[1, 1], self.lonpole,
+                         0.0 if self.proj == 'TAN' else 1.0, 0.0, 0.0], dtype=np.float64)
+
+    def celestial_pix2world_ref(self):
+        """(lon, lat) of the reference pixel -- by construction CRVAL."""
+        return self.crval[0], self.crval[1]
+
+    def to_header(self):
+        hdr = {}
+        for i in range(3):
+            n = i + 1
+            hdr['CTYPE%d' % n] = self.ctype[i]
+            hdr['CRVAL%d' % n] = float(self.crval[i])
+            hdr['CRPIX%d' % n] = float(self.crpix[i])
+            hdr['CDELT%d' % n] = float(self.cdelt[i])
+            hdr['CUNIT%d' % n] = self.cunit[i]
+            for j in range(3):
+                if self.pc[i, j] != (1.0 if i == j else 0.0):
+                    hdr['PC%d_%d' % (n, j + 1)] = float(self.pc[i, j])
+        hdr['LONPOLE'] = self.lonpole
+        return hdr
+
+    def celestial(self):
+        """2-D WCS description left after dropping the spectral axis (wcs_utils.py:28-45)."""
+        return CelestialWCS(self.ctype[:2], self.crval[:2].copy(), self.crpix[:2].copy(),
+                            self.cdelt[:2].copy(), self.pc[:2, :2].copy(), self.lonpole)
+
+    def drop_axis(self, np_axis):
+        """WCS of a projection along numpy axis ``np_axis`` (0 spectral, 1 lat, 2 lon)."""
+        if np_axis == 0:
+            return self.celestial()
+        keep = [i for i in range(3) if i != 2 - np_axis]
+        return AxesWCS([self.ctype[i] for i in keep], self.crval[keep].copy(), self.crpix[keep].copy(),
+                       self.cdelt[keep].copy(), [self.cunit[i] for i in keep])
+
+
+class CelestialWCS(object):
+    def __init__(self, ctype, crval, crpix, cdelt, pc, lonpole):
+        self.ctype, self.crval, self.crpix, self.cdelt, self.pc, self.lonpole = ctype, crval, crpix, cdelt, pc, lonpole
+        self.naxis = 2
+
+    def to_header(self):
+        hdr = {}
+        for i in range(2):
+            n = i + 1
+            hdr['CTYPE%d' % n] = self.ctype[i]
+            hdr['CRVAL%d' % n] = float(self.crval[i])
+            hdr['CRPIX%d' % n] = float(self.crpix[i])
+            hdr['CDELT%d' % n] = float(self.cdelt[i])
+            hdr['CUNIT%d' % n] = 'deg'
+        return hdr
+
+
+class AxesWCS(object):
+    def __init__(self, ctype, crval, crpix, cdelt, cunit):
+        self.ctype, self.crval, self.crpix, self.cdelt, self.cunit = ctype, crval, crpix, cdelt, cunit
+        self.naxis = len(ctype)
+
+    def to_header(self):
+        hdr = {}
+        for i in range(self.naxis):
+            n = i + 1
+            hdr['CTYPE%d' % n] = self.ctype[i]
+            hdr['CRVAL%d' % n] = float(self.crval[i])
+            hdr['CRPIX%d' % n] = float(self.crpix[i])
+            hdr['CDELT%d' % n] = float(self.cdelt[i])
+            hdr['CUNIT%d' % n] = self.cunit[i]
+        return hdr
+
+
+def as_cube_wcs(w):
+    if isinstance(w, CubeWCS):
+        return w
+    if hasattr(w, 'wcs') and hasattr(w.wcs, 'crval'):
+        return CubeWCS.from_astropy(w)
+    if hasattr(w, 'get') and hasattr(w, 'keys'):
+        return CubeWCS.from_header(w)
+    # duck-typed (e.g. the test oracle's WCS object): same attribute names
+    if all(hasattr(w, a) for a in ('ctype', 'crval', 'crpix', 'cdelt', 'cunit', 'pc')):
+        out = CubeWCS(list(w.ctype), np.array(w.crval), np.array(w.crpix), np.array(w.cdelt),
+                      list(w.cunit), pc=np.array(w.pc), lonpole=getattr(w, 'lonpole', None))
+        return out
+    raise TypeError("cannot interpret %r as a cube WCS" % (type(w),))
