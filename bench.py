@@ -59,7 +59,7 @@ class ClockSampler(object):
             os.close(fd)
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+                 '-lms', '50'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -355,10 +355,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cpu-rows', type=int, default=32, help='rows of the cube in the bounded CPU sample')
+    ap.add_argument('--cpu-rows', type=int, default=128, help='rows of the cube in the bounded CPU sample')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

@@ -62,11 +62,11 @@ template <int WANT>
 __device__ __forceinline__ void finalize(const MomParams &p, int64_t o, double s0, double s1, double s2, int cnt) {
     const bool any = cnt > 0;
     const double mean = s1 / s0;                        // offset from K; 0/0 -> NaN
-    if (WANT & SC_WANT_M0) p.m0[o] = any ? s0 * p.pix_size : nan64();
-    if (WANT & SC_WANT_M1) p.m1[o] = any ? (p.K + mean) + p.m1_offset : nan64();
+    if ((WANT & SC_WANT_M0) && p.m0) p.m0[o] = any ? s0 * p.pix_size : nan64();
+    if ((WANT & SC_WANT_M1) && p.m1) p.m1[o] = any ? (p.K + mean) + p.m1_offset : nan64();
     // a ray with a single included voxel has zero spread by construction (the reference gets
     // ~1e-26 from (x - M1)^2); the raw-sum form would leave +-1 ulp of d^2 here
-    if (WANT & SC_WANT_M2) p.m2[o] = any ? ((cnt == 1 && s0 != 0.0) ? 0.0 : s2 / s0 - mean * mean) : nan64();
+    if ((WANT & SC_WANT_M2) && p.m2) p.m2[o] = any ? ((cnt == 1 && s0 != 0.0) ? 0.0 : s2 / s0 - mean * mean) : nan64();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -308,9 +308,10 @@ moment_central_kernel(const __grid_constant__ CentralParams p) {
 template <int VEC, int UNROLL, int MODE>
 static cudaError_t launch_moments_want(const MomParams &p, int want, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
     const int hi = (want & SC_WANT_M2) ? 2 : (want & SC_WANT_M1) ? 1 : 0;
-    if (hi == 2)      moments_axis0_kernel<VEC, UNROLL, MODE, 7><<<grid, block, smem, s>>>(p);
-    else if (hi == 1) moments_axis0_kernel<VEC, UNROLL, MODE, 3><<<grid, block, smem, s>>>(p);
-    else              moments_axis0_kernel<VEC, UNROLL, MODE, 1><<<grid, block, smem, s>>>(p);
+    // M1-only requests run the M0|M1|M2 instantiation: ptxas turns the two-op predicated body of
+    // an M0|M1 variant into selects + spills, and it measured slower than the three-op one.
+    if (hi >= 1) moments_axis0_kernel<VEC, UNROLL, MODE, 7><<<grid, block, smem, s>>>(p);
+    else         moments_axis0_kernel<VEC, UNROLL, MODE, 1><<<grid, block, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -340,8 +341,7 @@ static cudaError_t launch_tma_one(const MomParams &p, unsigned grid, cudaStream_
 template <int CB, int STAGES, int MODE>
 static cudaError_t launch_tma_want(const MomParams &p, int want, unsigned grid, cudaStream_t s) {
     const int hi = (want & SC_WANT_M2) ? 2 : (want & SC_WANT_M1) ? 1 : 0;
-    if (hi == 2) return launch_tma_one<CB, STAGES, MODE, 7>(p, grid, s);
-    if (hi == 1) return launch_tma_one<CB, STAGES, MODE, 3>(p, grid, s);
+    if (hi >= 1) return launch_tma_one<CB, STAGES, MODE, 7>(p, grid, s);   // see launch_moments_want
     return launch_tma_one<CB, STAGES, MODE, 1>(p, grid, s);
 }
 
