@@ -1,0 +1,472 @@
+// spatial_smooth.cu -- per-channel 2-D NaN-interpolating convolution.
+//
+// Replaces `convolve(image, kernel2d, normalize_kernel=True)` applied to every channel
+// (spectral_cube.py:2808-2842 through :3049-3101 and :161-172; dask_spectral_cube.py:962-993).
+// Same astropy semantics as spectral_smooth.cu: true convolution, zero-filled boundary whose
+// zeros are valid samples, top/bot NaN interpolation, float64 numerator.
+//
+// Separable kernel (sep_march_kernel), used for outer-product kernels (Gaussian2DKernel):
+//   top = conv_y(conv_x(v * ok)), bot = conv_y(conv_x(ok)) are both exactly separable.
+//   A CTA owns a strip of SP_TX columns of one channel and MARCHES down the rows in blocks of
+//   R = 8: a producer warp streams the raw rows (strip + horizontal halo) into a shared-memory
+//   ring with cp.async.bulk (TMA) + mbarriers; the compute warps (1) apply mask/fill in place,
+//   (2) run the row pass with register blocking (a thread makes 8 adjacent outputs from 8+2H
+//   inputs read as float4) into a ring of row-passed lines {top f64, bot f32, centre f32},
+//   (3) run the column pass for the block that now has its 2H neighbours (a thread makes 8
+//   vertically adjacent outputs from 8+2H ring lines) and stores.  Every input row is
+//   row-passed once, so the float64 work is 2(2H+1) FMAs per voxel -- the float64 pipe, not HBM,
+//   bounds this kernel.  The denominator runs on the float32 pipe (it only enters the result
+//   as a ratio, so its rounding is a pure relative error of ~1e-7).
+//   Row sharding: rows above/below the shard come from `halo_top` / `halo_bot` (the
+//   neighbouring ranks' filled edge rows) or are zero at the image boundary.
+//
+// Direct kernel (direct2d_kernel): any odd x odd kernel (Tophat2DKernel, rotated beams), one
+// thread per output, taps in shared memory, input through L1/L2.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace scb {
+
+int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
+int env_int(const char *name, int dflt);
+
+constexpr int SP_TX = 128;               // strip width = compute threads
+constexpr int SP_HP = 16;                // horizontal halo carried in the raw ring (>= H, multiple of 4)
+constexpr int SP_W = SP_TX + 2 * SP_HP;  // raw row width in floats
+constexpr int SP_R = 8;                  // rows per block
+constexpr int SP_RS = 3;                 // raw ring stages
+constexpr int SP_THREADS = SP_TX + 32;
+constexpr int SP_MAX_TAPS = 2 * 16 + 1;
+
+struct SpatialParams {
+    const float *in;
+    void *out;
+    int64_t nchan, ny, nx;
+    int64_t stride_c, stride_y, out_stride_c, out_stride_y;
+    const float *halo_top, *halo_bot;    // (nchan, halo_rows, nx) filled rows or NULL
+    int halo_rows;
+    int strips_per_row;                  // strips across x
+    int rows_per_cta;                    // rows of the shard one CTA marches over
+    int chunks;                          // row chunks per (channel, strip)
+    float fill;
+    double ksum;                         // sum of the normalised 2-D kernel (~1)
+    double ty[SP_MAX_TAPS], tx[SP_MAX_TAPS];     // normalised factors, centred in 2H+1, zero padded
+    float tyf[SP_MAX_TAPS], txf[SP_MAX_TAPS];
+    const uint8_t *passthrough;          // (nchan) 1 = copy the filled plane through; may be NULL
+    DevMask mask;
+};
+
+template <int NB>
+struct SpatialSmem {
+    double top[NB * SP_R][SP_TX];
+    float bot[NB * SP_R][SP_TX];
+    float ctr[NB * SP_R][SP_TX];
+    float raw[SP_RS][SP_R][SP_W];
+    uint64_t full[SP_RS];
+    uint64_t empty[SP_RS];
+};
+
+__device__ __forceinline__ bool mask_include_rt(const DevMask &m, float v, int64_t c, int64_t y, int64_t x) {
+    if (m.mode == MODE_NONE) return true;
+    if (m.mode == MODE_INTERVAL) return (v > m.lo) & (v < m.hi);
+    return eval_mask_generic(m.prog, v, c, y, x);
+}
+
+__device__ __forceinline__ void compute_bar() {          // barrier among the SP_TX compute threads only
+    asm volatile("bar.sync 1, %0;" :: "n"(SP_TX) : "memory");
+}
+
+template <int H, int OUT64>
+__global__ void __launch_bounds__(SP_THREADS)
+sep_march_kernel(const __grid_constant__ SpatialParams p) {
+    constexpr int NT = 2 * H + 1;
+    constexpr int HB = (H + SP_R - 1) / SP_R;            // halo in blocks
+    constexpr int NB = 2 * HB + 2;                       // ring of row-passed blocks
+    constexpr int NIN_X = SP_R + 2 * SP_HP;              // 40 inputs per row-pass thread (aligned superset)
+    constexpr int NIN_Y = SP_R + 2 * H;
+    static_assert(H <= SP_HP, "horizontal halo too small");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpatialSmem<NB> &sm = *reinterpret_cast<SpatialSmem<NB> *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    // blockIdx.x = ((c * chunks) + chunk) * strips + strip
+    int64_t bid = blockIdx.x;
+    const int strip = (int)(bid % p.strips_per_row); bid /= p.strips_per_row;
+    const int chunk = (int)(bid % p.chunks);
+    const int64_t c = bid / p.chunks;
+    const int64_t x0 = (int64_t)strip * SP_TX;
+    const int64_t ya = (int64_t)chunk * p.rows_per_cta;
+    const int64_t yb = min(p.ny, ya + p.rows_per_cta);
+    const int nout_blk = (int)((yb - ya + SP_R - 1) / SP_R);
+    const int nblk = nout_blk + 2 * HB;                  // blocks to row-pass
+    const int64_t y_first = ya - (int64_t)HB * SP_R;     // first row of block 0
+
+    // clipped horizontal window of the raw rows
+    const int64_t xl = max((int64_t)0, x0 - SP_HP), xr = min(p.nx, x0 + SP_TX + SP_HP);
+    const int col_off = (int)(xl - (x0 - SP_HP));        // where the copy lands in the raw row
+    const uint32_t row_bytes = (uint32_t)(xr - xl) * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < SP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SP_TX / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == SP_TX / 32) {
+        // ---------------- producer warp: raw rows of block b -> raw[b % RS] ----------------
+        const uint64_t pol = l2_evict_first_policy();
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b % SP_RS;
+            if (b >= SP_RS) mbar_wait(&sm.empty[s], ((b / SP_RS) - 1) & 1);
+            const float *src = nullptr;
+            if (lane < SP_R) {
+                const int64_t y = y_first + (int64_t)b * SP_R + lane;
+                if (y >= 0 && y < p.ny) src = p.in + c * p.stride_c + y * p.stride_y + xl;
+                else if (y < 0 && p.halo_top && y >= -p.halo_rows)
+                    src = p.halo_top + (c * p.halo_rows + (p.halo_rows + y)) * p.nx + xl;
+                else if (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows)
+                    src = p.halo_bot + (c * p.halo_rows + (y - p.ny)) * p.nx + xl;
+            }
+            const unsigned have = __ballot_sync(0xffffffffu, src != nullptr);
+            if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)__popc(have) * row_bytes);
+            __syncwarp();
+            if (src) tma_load_1d(&sm.raw[s][lane][col_off], src, row_bytes, &sm.full[s], pol);
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    // float32 denominator of a window with nothing missing, accumulated in the same order as below
+    float botx_full = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) botx_full = fmaf(p.txf[k], 1.0f, botx_full);
+    float bot_full = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) bot_full = fmaf(p.tyf[k], botx_full, bot_full);
+    const bool pass = p.passthrough && p.passthrough[c];
+
+    const int rrow = tid >> 4;            // row-pass mapping: row of the block
+    const int roct = tid & 15;            // ... and octet of columns
+
+    for (int b = 0; b < nblk; ++b) {
+        const int s = b % SP_RS;
+        const int64_t yblk = y_first + (int64_t)b * SP_R;
+        mbar_wait(&sm.full[s], (b / SP_RS) & 1);
+
+        // (1) in place: zero what the copy did not cover, apply mask/fill to the cube's own rows
+        for (int e = tid; e < SP_R * SP_W; e += SP_TX) {
+            const int r = e / SP_W, col = e - r * SP_W;
+            const int64_t y = yblk + r, x = x0 - SP_HP + col;
+            const bool in_x = x >= 0 && x < p.nx;
+            const bool own = y >= 0 && y < p.ny;
+            const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
+            float v = 0.0f;                                         // outside the image: a valid zero
+            if (in_x && (own || halo)) {
+                v = sm.raw[s][r][col];
+                if (own && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+            }
+            sm.raw[s][r][col] = v;
+        }
+        compute_bar();
+
+        // (2) row pass: 8 adjacent outputs of row `rrow` from 40 aligned inputs
+        {
+            double w[NIN_X];
+            float okf[NIN_X];
+            bool anynan = false;
+#pragma unroll
+            for (int q = 0; q < NIN_X / 4; ++q) {
+                const float4 f = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][roct * 8 + q * 4]);
+                const float a[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    const bool isn = a[z] != a[z];
+                    anynan |= isn;
+                    w[q * 4 + z] = isn ? 0.0 : (double)a[z];
+                    okf[q * 4 + z] = isn ? 0.0f : 1.0f;
+                }
+            }
+            const int slot = (b % NB) * SP_R + rrow;
+#pragma unroll
+            for (int j = 0; j < SP_R; ++j) {
+                double top = 0.0;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) top = fma(p.tx[k], w[j + SP_HP + H - k], top);
+                float bot = botx_full;
+                if (anynan) {
+                    bot = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) bot = fmaf(p.txf[k], okf[j + SP_HP + H - k], bot);
+                }
+                sm.top[slot][roct * 8 + j] = top;
+                sm.bot[slot][roct * 8 + j] = bot;
+            }
+            // centre values (filled input) for the bot == 0 / pass-through cases
+            const float4 c0 = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][SP_HP + roct * 8]);
+            const float4 c1 = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][SP_HP + roct * 8 + 4]);
+            *reinterpret_cast<float4 *>(&sm.ctr[slot][roct * 8]) = c0;
+            *reinterpret_cast<float4 *>(&sm.ctr[slot][roct * 8 + 4]) = c1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        compute_bar();
+
+        // (3) column pass for output block j = b - 2 HB (its rows are block j + HB of the march)
+        if (b >= 2 * HB) {
+            const int jb = b - HB;                                   // march-block holding the output rows
+            const int64_t yout = y_first + (int64_t)jb * SP_R;
+            double w[NIN_Y];
+            float bt[NIN_Y];
+#pragma unroll
+            for (int i = 0; i < NIN_Y; ++i) {
+                // ring line of march-row jb*R - H + i
+                const int mr = jb * SP_R - H + i;
+                const int slot = ((mr / SP_R) % NB) * SP_R + (mr % SP_R);
+                w[i] = sm.top[slot][tid];
+                bt[i] = sm.bot[slot][tid];
+            }
+            const int64_t x = x0 + tid;
+#pragma unroll
+            for (int r = 0; r < SP_R; ++r) {
+                const int64_t y = yout + r;
+                double top = 0.0;
+                float bot = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    top = fma(p.ty[k], w[r + 2 * H - k], top);
+                    bot = fmaf(p.tyf[k], bt[r + 2 * H - k], bot);
+                }
+                if (y < yb && x < p.nx) {
+                    const int mr = jb * SP_R + r;
+                    const float centre = sm.ctr[((mr / SP_R) % NB) * SP_R + (mr % SP_R)][tid];
+                    double res;
+                    if (bot == bot_full) res = top;
+                    else if (bot == 0.0f) res = (double)centre;
+                    else res = top / (p.ksum * ((double)bot / (double)bot_full));
+                    if (pass) res = (double)centre;
+                    if (OUT64) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
+                    else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
+                }
+            }
+        }
+    }
+}
+
+// ---- direct 2-D kernel: any odd x odd taps ------------------------------------------------------------
+struct DirectParams {
+    SpatialParams sp;
+    const double *taps;      // device, normalised, (nty, ntx) row-major
+    int nty, ntx;
+};
+
+template <int OUT64>
+__global__ void __launch_bounds__(256)
+direct2d_kernel(const __grid_constant__ DirectParams d) {
+    const SpatialParams &p = d.sp;
+    extern __shared__ double staps[];
+    for (int i = threadIdx.x; i < d.nty * d.ntx; i += blockDim.x) staps[i] = d.taps[i];
+    __syncthreads();
+    const int64_t per_chan = p.ny * p.nx;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.nchan * per_chan) return;
+    const int64_t c = g / per_chan;
+    const int64_t rem = g - c * per_chan;
+    const int64_t y = rem / p.nx, x = rem - y * p.nx;
+    const int hy = d.nty >> 1, hx = d.ntx >> 1;
+    double top = 0.0, bot = 0.0;
+    float centre = 0.0f;
+    for (int ky = 0; ky < d.nty; ++ky) {
+        const int64_t yy = y + hy - ky;
+        for (int kx = 0; kx < d.ntx; ++kx) {
+            const int64_t xx = x + hx - kx;
+            float v = 0.0f;
+            if (xx >= 0 && xx < p.nx) {
+                if (yy >= 0 && yy < p.ny) {
+                    v = __ldg(p.in + c * p.stride_c + yy * p.stride_y + xx);
+                    if (!mask_include_rt(p.mask, v, c, yy, xx)) v = p.fill;
+                } else if (yy < 0 && p.halo_top && yy >= -p.halo_rows) {
+                    v = __ldg(p.halo_top + (c * p.halo_rows + (p.halo_rows + yy)) * p.nx + xx);
+                } else if (yy >= p.ny && p.halo_bot && yy < p.ny + p.halo_rows) {
+                    v = __ldg(p.halo_bot + (c * p.halo_rows + (yy - p.ny)) * p.nx + xx);
+                }
+            }
+            if (ky == hy && kx == hx) centre = v;
+            const double k = staps[ky * d.ntx + kx];
+            if (v == v) { top = fma(k, (double)v, top); bot += k; }
+        }
+    }
+    double res = (bot == 0.0) ? (double)centre : top / bot;
+    if (p.passthrough && p.passthrough[c]) res = (double)centre;
+    if (OUT64) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
+    else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
+}
+
+template <int H, int OUT64>
+static cudaError_t launch_sep_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    constexpr int HB = (H + SP_R - 1) / SP_R;
+    constexpr int NB = 2 * HB + 2;
+    auto kern = sep_march_kernel<H, OUT64>;
+    const size_t smem = sizeof(SpatialSmem<NB>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, SP_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int OUT64>
+static cudaError_t launch_sep_h(const SpatialParams &p, int h, unsigned grid, cudaStream_t s) {
+    if (h <= 2)  return launch_sep_one<2, OUT64>(p, grid, s);
+    if (h <= 4)  return launch_sep_one<4, OUT64>(p, grid, s);
+    if (h <= 6)  return launch_sep_one<6, OUT64>(p, grid, s);
+    if (h <= 8)  return launch_sep_one<8, OUT64>(p, grid, s);
+    if (h <= 10) return launch_sep_one<10, OUT64>(p, grid, s);
+    if (h <= 12) return launch_sep_one<12, OUT64>(p, grid, s);
+    if (h <= 14) return launch_sep_one<14, OUT64>(p, grid, s);
+    return launch_sep_one<16, OUT64>(p, grid, s);
+}
+
+static int fill_common(SpatialParams &p, const float *in, void *out, int out_dtype,
+                       int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y,
+                       int64_t out_stride_c, int64_t out_stride_y, const sc_mask_desc *mask, double fill,
+                       const float *halo_top, const float *halo_bot, int halo_rows, int plane_passthrough) {
+    int rc = check_cube_args(in, nchan, ny, nx, stride_c, stride_y);
+    if (rc) return rc;
+    SC_CHECK_ARG(out != nullptr && (const void *)in != out, "out is NULL or aliases the input (spatial smoothing is out of place)");
+    SC_CHECK_ARG(out_dtype == SC_F32 || out_dtype == SC_F64, "out_dtype must be SC_F32 or SC_F64");
+    SC_CHECK_ARG(out_stride_y >= nx && out_stride_c >= out_stride_y, "bad output strides");
+    SC_CHECK_ARG(halo_rows >= 0, "halo_rows must be >= 0");
+    SC_CHECK_ARG(halo_rows > 0 || (!halo_top && !halo_bot), "halo buffers given but halo_rows == 0");
+    p.in = in; p.out = out; p.nchan = nchan; p.ny = ny; p.nx = nx;
+    p.stride_c = stride_c; p.stride_y = stride_y; p.out_stride_c = out_stride_c; p.out_stride_y = out_stride_y;
+    p.halo_top = halo_top; p.halo_bot = halo_bot; p.halo_rows = halo_rows;
+    p.fill = (float)fill;
+    p.passthrough = nullptr;
+    if (plane_passthrough && mask && mask->n_nodes > 0 && fill == fill) {
+        set_error("plane_passthrough with a finite fill value is not supported yet");
+        return SC_ERR_UNSUPPORTED;
+    }
+    return build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
+                                     int64_t nchan, int64_t ny, int64_t nx,
+                                     int64_t stride_c, int64_t stride_y,
+                                     int64_t out_stride_c, int64_t out_stride_y,
+                                     const sc_mask_desc *mask, double fill,
+                                     const double *taps_y, int ntaps_y, const double *taps_x, int ntaps_x,
+                                     const float *halo_top, const float *halo_bot, int halo_rows,
+                                     int plane_passthrough,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
+    SpatialParams p{};
+    int rc = fill_common(p, in, out, out_dtype, nchan, ny, nx, stride_c, stride_y, out_stride_c, out_stride_y,
+                         mask, fill, halo_top, halo_bot, halo_rows, plane_passthrough);
+    if (rc) return rc;
+    SC_CHECK_ARG(taps_y && taps_x, "taps are NULL");
+    SC_CHECK_ARG(ntaps_y >= 1 && (ntaps_y & 1) && ntaps_x >= 1 && (ntaps_x & 1), "Kernel size must be odd in all axes.");
+    const int hy = ntaps_y >> 1, hx = ntaps_x >> 1;
+    const int h = hy > hx ? hy : hx;
+    SC_CHECK_ARG(halo_rows == 0 || halo_rows >= hy, "halo_rows=%d is smaller than the kernel half-height %d", halo_rows, hy);
+    double sy = 0.0, sx = 0.0;
+    for (int k = 0; k < ntaps_y; ++k) sy += taps_y[k];
+    for (int k = 0; k < ntaps_x; ++k) sx += taps_x[k];
+    SC_CHECK_ARG(fabs(sy * sx) > 1e-8, "The kernel can't be normalized, because its sum is close to zero.");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool aligned = ((uintptr_t)in % 16 == 0) && stride_c % 4 == 0 && stride_y % 4 == 0 && nx % 4 == 0 &&
+                         (!halo_top || (uintptr_t)halo_top % 16 == 0) && (!halo_bot || (uintptr_t)halo_bot % 16 == 0);
+    const int choice = env_int("SC_SPATIAL_KERNEL", 0);          // 0 auto, 1 direct, 2 march
+    if (h <= 16 && aligned && choice != 1) {
+        const int H = h <= 2 ? 2 : h <= 4 ? 4 : h <= 6 ? 6 : h <= 8 ? 8 : h <= 10 ? 10 : h <= 12 ? 12 : h <= 14 ? 14 : 16;
+        double ksy = 0.0, ksx = 0.0;
+        for (int k = 0; k < SP_MAX_TAPS; ++k) { p.ty[k] = p.tx[k] = 0.0; p.tyf[k] = p.txf[k] = 0.0f; }
+        for (int k = 0; k < ntaps_y; ++k) { p.ty[k + H - hy] = taps_y[k] / sy; ksy += p.ty[k + H - hy]; p.tyf[k + H - hy] = (float)p.ty[k + H - hy]; }
+        for (int k = 0; k < ntaps_x; ++k) { p.tx[k + H - hx] = taps_x[k] / sx; ksx += p.tx[k + H - hx]; p.txf[k + H - hx] = (float)p.tx[k + H - hx]; }
+        p.ksum = ksy * ksx;
+        p.strips_per_row = (int)cdiv(nx, SP_TX);
+        // row chunks: enough CTAs to fill the chip, each long enough to amortise the 2H-row run-in
+        int64_t chunks = 1;
+        const int64_t base = nchan * p.strips_per_row;
+        while (base * chunks < 148 * 4 && ny / (chunks * 2) >= 8 * h + 16) chunks *= 2;
+        const int forced = env_int("SC_SPATIAL_CHUNKS", 0);
+        if (forced > 0) chunks = forced;
+        p.rows_per_cta = (int)(cdiv(cdiv(ny, chunks), SP_R) * SP_R);
+        p.chunks = (int)cdiv(ny, p.rows_per_cta);
+        const int64_t grid = base * p.chunks;
+        SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
+        LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
+        cudaError_t e = out_dtype == SC_F64 ? launch_sep_h<1>(p, H, (unsigned)grid, s) : launch_sep_h<0>(p, H, (unsigned)grid, s);
+        if (e != cudaSuccess) return cuda_fail(e, "sep_march_kernel launch");
+        return SC_OK;
+    }
+    // fall back to the direct kernel on the outer product
+    const int nt = ntaps_y * ntaps_x;
+    const size_t need = (size_t)nt * 8 + 256;
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return SC_ERR_WORKSPACE;
+    }
+    SC_CHECK_ARG(nt <= 6000, "kernel too large for the direct path (%d taps)", nt);
+    double *host = (double *)malloc((size_t)nt * 8);
+    for (int a = 0; a < ntaps_y; ++a) for (int b = 0; b < ntaps_x; ++b) host[a * ntaps_x + b] = (taps_y[a] / sy) * (taps_x[b] / sx);
+    double *tdev = (double *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    cudaError_t ce = cudaMemcpyAsync(tdev, host, (size_t)nt * 8, cudaMemcpyHostToDevice, s);
+    free(host);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(taps)");
+    DirectParams d{p, tdev, ntaps_y, ntaps_x};
+    const int64_t total = nchan * ny * nx;
+    LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
+    if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+    else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+}
+
+extern "C" int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
+                                    int64_t nchan, int64_t ny, int64_t nx,
+                                    int64_t stride_c, int64_t stride_y,
+                                    int64_t out_stride_c, int64_t out_stride_y,
+                                    const sc_mask_desc *mask, double fill,
+                                    const double *taps, int ntaps_y, int ntaps_x,
+                                    const float *halo_top, const float *halo_bot, int halo_rows,
+                                    int plane_passthrough,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    SpatialParams p{};
+    int rc = fill_common(p, in, out, out_dtype, nchan, ny, nx, stride_c, stride_y, out_stride_c, out_stride_y,
+                         mask, fill, halo_top, halo_bot, halo_rows, plane_passthrough);
+    if (rc) return rc;
+    SC_CHECK_ARG(taps != nullptr, "taps is NULL");
+    SC_CHECK_ARG(ntaps_y >= 1 && (ntaps_y & 1) && ntaps_x >= 1 && (ntaps_x & 1), "Kernel size must be odd in all axes.");
+    SC_CHECK_ARG(halo_rows == 0 || halo_rows >= (ntaps_y >> 1), "halo_rows=%d is smaller than the kernel half-height %d", halo_rows, ntaps_y >> 1);
+    const int nt = ntaps_y * ntaps_x;
+    SC_CHECK_ARG(nt <= 6000, "kernel too large for the direct path (%d taps)", nt);
+    double sum = 0.0;
+    for (int i = 0; i < nt; ++i) sum += taps[i];
+    SC_CHECK_ARG(fabs(sum) > 1e-8, "The kernel can't be normalized, because its sum is close to zero.");
+    const size_t need = (size_t)nt * 8 + 256;
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return SC_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    double *host = (double *)malloc((size_t)nt * 8);
+    for (int i = 0; i < nt; ++i) host[i] = taps[i] / sum;
+    double *tdev = (double *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    cudaError_t ce = cudaMemcpyAsync(tdev, host, (size_t)nt * 8, cudaMemcpyHostToDevice, s);
+    free(host);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(taps)");
+    DirectParams d{p, tdev, ntaps_y, ntaps_x};
+    const int64_t total = nchan * ny * nx;
+    LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
+    if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+    else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+}

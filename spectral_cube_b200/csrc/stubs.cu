@@ -10,21 +10,6 @@ extern "C" {
 int sc_moments_spatial(const float *, int64_t, int64_t, int64_t, int64_t, int64_t, int,
                        const sc_mask_desc *, const double *, double, int, double *, double *, double *, void *) { SC_STUB("sc_moments_spatial") }
 
-int sc_spectral_smooth(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                       const sc_mask_desc *, double, const double *, int, int, void *, size_t, void *) { SC_STUB("sc_spectral_smooth") }
-
-int sc_smooth_moments_axis0(const float *, int64_t, int64_t, int64_t, int64_t, int64_t, const sc_mask_desc *, double,
-                            const double *, int, int, const double *, double, double, int, double *, double *, double *,
-                            void *, size_t, void *) { SC_STUB("sc_smooth_moments_axis0") }
-
-int sc_spatial_smooth_sep(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                          const sc_mask_desc *, double, const double *, int, const double *, int,
-                          const float *, const float *, int, int, void *, size_t, void *) { SC_STUB("sc_spatial_smooth_sep") }
-
-int sc_spatial_smooth_2d(const float *, void *, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                         const sc_mask_desc *, double, const double *, int, int,
-                         const float *, const float *, int, int, void *, size_t, void *) { SC_STUB("sc_spatial_smooth_2d") }
-
 int sc_spectral_interp(const float *, void *, int, uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
                        const sc_mask_desc *, double, const double *, const double *, int, double, int, int, int,
                        void *, size_t, void *) { SC_STUB("sc_spectral_interp") }

@@ -40,6 +40,10 @@ class BeamUnitsError(Exception):
     pass
 
 
+class UnitsError(ValueError):
+    """Stands in for astropy.units.UnitsError when astropy is absent."""
+
+
 def _torch():
     return _lib.require_cuda()
 
@@ -69,7 +73,9 @@ class BaseSpectralCube(object):
             raise ValueError("data should be a 3-d array")
         if t.stride(2) != 1:
             t = t.contiguous()
-        self._data = t
+        self._data_t = t
+        self._data_hi = None            # float64 tensor when the numpy-class semantics produce one
+        self._pending = None            # lazy op recorded by DaskSpectralCube (see spectral_smooth)
         self._wcs = as_cube_wcs(wcs)
         if mask is not None and not isinstance(mask, MaskBase):
             mask = BooleanArrayMask(np.asarray(mask, dtype=bool), self._wcs, shape=tuple(t.shape))
@@ -84,7 +90,17 @@ class BaseSpectralCube(object):
         self._spectral_unit = spectral_unit if spectral_unit is not None else self._wcs.cunit[2]
         self._spectral_scale = spectral_unit_scale(self._wcs.cunit[2], self._spectral_unit)
         self._workspace = None
-        self._pending = None            # lazy op recorded by DaskSpectralCube (see spectral_smooth)
+
+    @property
+    def _data(self):
+        """float32 device tensor of the voxels; a pending lazy op is materialised on first use."""
+        if self._data_t is None:
+            self._data_t = self._pending.materialize()
+        return self._data_t
+
+    @property
+    def _shape(self):
+        return tuple(self._data_t.shape) if self._data_t is not None else self._pending.shape
 
     # -- construction ------------------------------------------------------------------------
     def _new_cube_with(self, data=None, wcs=None, mask=None, meta=None, fill_value=None,
@@ -92,6 +108,9 @@ class BaseSpectralCube(object):
         """spectral_cube.py:244-289"""
         cls = cls or type(self)
         cube = cls.__new__(cls)
+        still_lazy = data is None and self._data_t is None
+        if still_lazy:
+            data = self._pending.source._data            # placeholder; replaced below
         BaseSpectralCube.__init__(
             cube,
             data=self._data if data is None else data,
@@ -102,12 +121,14 @@ class BaseSpectralCube(object):
             header=self._header, allow_huge_operations=self.allow_huge_operations,
             unit=self._unit if unit is None else unit,
             spectral_unit=self._spectral_unit if spectral_unit is None else spectral_unit)
+        if still_lazy:
+            cube._data_t, cube._pending = None, self._pending
         return cube
 
     # -- basic properties ------------------------------------------------------------------------
     @property
     def shape(self):
-        return tuple(self._data.shape)
+        return self._shape
 
     @property
     def size(self):
@@ -227,6 +248,13 @@ class BaseSpectralCube(object):
         return out
 
     def _get_filled_data(self, view=(), fill=np.nan, **kwargs):
+        if self._data_hi is not None:
+            torch = _torch()
+            if self._mask is None:
+                return self._data_hi.cpu().numpy()[view]
+            inc = self._mask._include_tensor(self._data).bool()
+            return torch.where(inc, self._data_hi, torch.full((), float(fill), dtype=torch.float64,
+                                                              device=self._data_hi.device)).cpu().numpy()[view]
         return self._filled_tensor(fill).cpu().numpy()[view]
 
     @property
@@ -239,7 +267,7 @@ class BaseSpectralCube(object):
 
     @property
     def unmasked_data(self):
-        return _Sliceable(lambda view: self._data.cpu().numpy()[view])
+        return _Sliceable(lambda view: (self._data_hi if self._data_hi is not None else self._data).cpu().numpy()[view])
 
     def flattened(self, slice=(), weights=None):
         return self._mask._flattened(self._data, view=slice) if self._mask is not None \
@@ -271,13 +299,108 @@ class BaseSpectralCube(object):
             self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self._data.device)
         return self._workspace
 
+    # -- smoothing (spectral_cube.py:3186-3222, 2808-2842; dask_spectral_cube.py:880-917, 962-993) ----
+    @staticmethod
+    def _kernel_array(kernel, ndim):
+        arr = kernel.array if hasattr(kernel, 'array') else kernel
+        if hasattr(arr, 'unit'):
+            # spectral_cube.py:3212-3214
+            raise UnitsError("The convolution kernel should be defined without a unit.")
+        arr = np.asarray(arr, dtype=np.float64)
+        if arr.ndim != ndim:
+            raise Exception("array and kernel have differing number of dimensions.")
+        if any(n % 2 == 0 for n in arr.shape):
+            raise Exception("Kernel size must be odd in all axes.")
+        return arr
+
+    def _smooth_fill(self):
+        """Fill value masked voxels take before convolving (numpy class: the cube's fill value,
+        spectral_cube.py:3085/3139; the dask spectral path hard-codes NaN, dask:816-823)."""
+        return self._fill_value
+
+    def _run_spectral_smooth(self, taps, out_dtype):
+        torch = _torch()
+        lib = _lib.load()
+        src = self._data
+        nchan, ny, nx = self.shape
+        out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
+                          device=src.device)
+        desc, keep = self._mask_desc()
+        ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPECTRAL_SMOOTH, nchan, ny, nx, len(taps)))
+        tarr, tptr = _lib.as_double_array(taps)
+        _lib.check(lib.sc_spectral_smooth(
+            src.data_ptr(), out.data_ptr(), out_dtype, nchan, ny, nx, src.stride(0), src.stride(1),
+            out.stride(0), out.stride(1), desc, float(self._smooth_fill()), tptr, len(taps), 0,
+            ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    def _new_cube_from_f64(self, out64):
+        cube = self._new_cube_with(data=out64.to(_torch().float32))
+        cube._data_hi = out64                   # the numpy class returns a float64 cube (:2953/:2963)
+        return cube
+
+    def spectral_smooth(self, kernel, convolve=None, verbose=0, use_memmap=True, num_cores=None, **kwargs):
+        """Smooth the cube along the spectral dimension; the mask is left unchanged."""
+        taps = self._kernel_array(kernel, 1)
+        return self._new_cube_from_f64(self._run_spectral_smooth(taps, _lib.F64))
+
+    def check_jybeam_smoothing(self, raise_error_jybm=True):
+        """base_class.py:116-140"""
+        if str(self._unit).replace(' ', '').lower() == 'jy/beam' and raise_error_jybm:
+            raise BeamUnitsError("Attempting to change the spatial resolution of a cube with Jy/beam units."
+                                 " To ignore this error, set `raise_error_jybm=False`.")
+
+    @staticmethod
+    def _separable_factors(k2d):
+        """(ky, kx) if the 2-D kernel is an outer product to float64 rounding, else None."""
+        cy, cx = k2d.shape[0] // 2, k2d.shape[1] // 2
+        piv = k2d[cy, cx]
+        if piv == 0:
+            return None
+        ky, kx = k2d[:, cx].copy(), k2d[cy, :] / piv
+        if np.max(np.abs(np.outer(ky, kx) - k2d)) <= 1e-14 * np.max(np.abs(k2d)):
+            return ky, kx
+        return None
+
+    def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0):
+        torch = _torch()
+        lib = _lib.load()
+        src = self._data
+        nchan, ny, nx = self.shape
+        out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
+                          device=src.device)
+        desc, keep = self._mask_desc()
+        ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPATIAL_SMOOTH, nchan, ny, nx, k2d.size))
+        ht = halo_top.data_ptr() if halo_top is not None else None
+        hb = halo_bot.data_ptr() if halo_bot is not None else None
+        common = (src.data_ptr(), out.data_ptr(), out_dtype, nchan, ny, nx, src.stride(0), src.stride(1),
+                  out.stride(0), out.stride(1), desc, float(self._fill_value))
+        sep = self._separable_factors(k2d)
+        if sep is not None:
+            (ya, yp), (xa, xp) = _lib.as_double_array(sep[0]), _lib.as_double_array(sep[1])
+            _lib.check(lib.sc_spatial_smooth_sep(*common, yp, len(ya), xp, len(xa), ht, hb, int(halo_rows), 0,
+                                                 ws.data_ptr(), ws.numel(), _stream()))
+        else:
+            ka, kp = _lib.as_double_array(k2d.ravel())
+            _lib.check(lib.sc_spatial_smooth_2d(*common, kp, k2d.shape[0], k2d.shape[1], ht, hb, int(halo_rows), 0,
+                                                ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    def spatial_smooth(self, kernel, convolve=None, raise_error_jybm=True, **kwargs):
+        """Smooth the image in each spatial-spatial plane of the cube."""
+        self.check_jybeam_smoothing(raise_error_jybm=raise_error_jybm)
+        k2d = self._kernel_array(kernel, 2)
+        if self._mirrors_dask:
+            return self._new_cube_with(data=self._run_spatial_smooth(k2d, _lib.F32))
+        return self._new_cube_from_f64(self._run_spatial_smooth(k2d, _lib.F64))
+
     # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
     def _moments_axis0_raw(self, want_bits):
         """Run the fused kernel; returns dict order -> float64 device tensor (ny, nx), with units
         folded in the way ``moment()`` does (M1 already carries the channel-0 world offset)."""
         torch = _torch()
         lib = _lib.load()
-        if self._pending is not None:
+        if self._pending is not None and self._data_t is None:
             return self._pending.moments(self, want_bits)
         nchan, ny, nx = self.shape
         dev = self._data.device
@@ -381,6 +504,45 @@ class BaseSpectralCube(object):
         return s._with(s.value * SIGMA2FWHM, s.unit)
 
 
+class _PendingSpectralSmooth(object):
+    """A spectral_smooth recorded but not yet run (the dask class is lazy, dask:880-917).  A moment
+    requested on the result runs the fused kernel and never writes the smoothed cube; any other
+    access materialises it (float32, dask:829)."""
+
+    def __init__(self, source, taps):
+        self.source, self.taps = source, taps
+        self.shape = source.shape
+
+    def materialize(self):
+        return self.source._run_spectral_smooth(self.taps, _lib.F32)
+
+    def moments(self, cube, want_bits):
+        torch = _torch()
+        lib = _lib.load()
+        src_cube = self.source
+        src = src_cube._data
+        nchan, ny, nx = self.shape
+        outs, ptrs = {}, []
+        for bit, order in ((1, 0), (2, 1), (4, 2)):
+            if want_bits & bit:
+                outs[order] = torch.empty((ny, nx), dtype=torch.float64, device=src.device)
+                ptrs.append(outs[order].data_ptr())
+            else:
+                ptrs.append(None)
+        # the smoothed cube keeps the OLD mask object; lowered against the source tensor it is the
+        # include mask of the original data (spectral_cube.py:3043-3045)
+        desc, keep = lower_mask(cube._mask, src)
+        wsb = lib.sc_workspace_bytes(_lib.OP_SMOOTH_MOMENTS, nchan, ny, nx, len(self.taps))
+        ws = cube._get_workspace(wsb)
+        xoff, xptr = _lib.as_double_array(cube._spectral_offsets())
+        tarr, tptr = _lib.as_double_array(self.taps)
+        _lib.check(lib.sc_smooth_moments_axis0(
+            src.data_ptr(), nchan, ny, nx, src.stride(0), src.stride(1), desc, float(src_cube._smooth_fill()),
+            tptr, len(self.taps), _lib.F32, xptr, float(cube._pix_size_slice(0)), cube._world0_spectral(),
+            want_bits, ptrs[0], ptrs[1], ptrs[2], ws.data_ptr(), ws.numel(), _stream()))
+        return outs
+
+
 class _Sliceable(object):
     def __init__(self, getter):
         self._getter = getter
@@ -416,6 +578,21 @@ class DaskSpectralCube(SpectralCube):
 
     def rechunk(self, *args, **kwargs):
         return self
+
+    def _smooth_fill(self):
+        return np.nan                        # dask_spectral_cube.py:816, 823
+
+    def spectral_smooth(self, kernel, convolve=None, save_to_tmp_dir=False, **kwargs):
+        """Lazy like the reference's dask class; ``save_to_tmp_dir=True`` computes straight away."""
+        taps = self._kernel_array(kernel, 1)
+        if self._mask is not None and self._pending is not None and self._data_t is None:
+            self._data                        # chain of lazy ops: materialise the inner one first
+        cube = self._new_cube_with()
+        cube._data_t = None
+        cube._pending = _PendingSpectralSmooth(self, taps)
+        if save_to_tmp_dir:
+            cube._data
+        return cube
 
 
 class _NullContext(object):

@@ -1,0 +1,240 @@
+"""
+GPU parity tests for spectral_smooth / spatial_smooth and the fused spectral_smooth -> moment
+chain.  Goldens: spectral_cube/tests/test_regrid.py:138-172 and
+spectral_cube/tests/test_spectral_cube.py:2363-2421; everything else against the CPU oracle
+(oracle/convolve.py restates astropy.convolution.convolve).  Tolerance 1e-5 relative.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle.convolve as oconv
+from tests.golden import reference_goldens as G
+from tests.helpers import oracle_cube, gpu_cube, assert_maps_close, RTOL
+from tests.test_moments_gpu import BENCH_WCS, _random_cube, quiet
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels():
+    import spectral_cube_b200 as scb
+    return scb
+
+
+def delta_pair(data, use_dask, flip=False):
+    w = dict(G.ADV_WCS)
+    if flip:
+        w['cdelt'] = [w['cdelt'][0], w['cdelt'][1], -w['cdelt'][2]]
+    return (gpu_cube(data, w, use_dask=use_dask, spectral_unit='km/s'),
+            oracle_cube(data, w, use_dask=use_dask, spectral_unit='km/s'))
+
+
+# ---- spectral_cube/tests/test_regrid.py:138-172 ----------------------------------------------------
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_spectral_smooth(use_dask):
+    scb = _kernels()
+    cube, _ = delta_pair(G.delta_522(), use_dask)
+    kernel = scb.Gaussian1DKernel(1.0)
+    result = cube.spectral_smooth(kernel)
+    assert kernel.array.size == 9
+    np.testing.assert_almost_equal(result.unmasked_data[:, 0, 0], kernel.array[2:-2], 4)
+    # dtype contract: numpy class -> float64 cube (:2953/:2963), dask class keeps float32 (:829)
+    assert result.unmasked_data[:].dtype == (np.float32 if use_dask else np.float64)
+    assert result.mask is cube.mask                      # mask object untouched (:3043-3045)
+
+
+def test_spectral_smooth_rejects_even_kernels_and_units():
+    scb = _kernels()
+    cube, _ = delta_pair(G.delta_522(), False)
+    with pytest.raises(Exception, match="odd"):
+        cube.spectral_smooth(np.ones(4))
+
+    class WithUnit(object):
+        class array(object):
+            unit = 'K'
+    with pytest.raises(Exception, match="without a unit"):
+        cube.spectral_smooth(WithUnit())
+
+
+# ---- oracle parity ----------------------------------------------------------------------------------
+@pytest.mark.parametrize('use_dask', [False, True])
+@pytest.mark.parametrize('ntaps', [1, 3, 5, 9, 13, 17, 21, 25, 33, 41])
+def test_spectral_smooth_matches_oracle(ntaps, use_dask):
+    scb = _kernels()
+    rng = np.random.default_rng(ntaps)
+    data = _random_cube((50, 6, 16), seed=100 + ntaps, nan_frac=0.04)
+    data[10:40, 2, 3] = np.nan                            # a long NaN run: bot == 0 inside for short kernels
+    taps = rng.random(ntaps) + 0.05                      # asymmetric on purpose: catches a missing flip
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=use_dask), oracle_cube(data, BENCH_WCS, use_dask=use_dask)
+    got = sc.spectral_smooth(scb.CustomKernel(taps)).unmasked_data[:]
+    want = oc.spectral_smooth(oconv.Kernel(taps))._data
+    assert got.dtype == want.dtype
+    assert_maps_close(got, want, rtol=RTOL, what='ntaps=%d' % ntaps)
+
+
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_spectral_smooth_gaussian_fwhm5_under_mask(use_dask):
+    """BASELINE config 3's kernel (17 taps) on a cube carrying a > threshold mask: masked voxels are
+    NaN-filled before convolving and interpolated over."""
+    scb = _kernels()
+    data = _random_cube((96, 5, 132), seed=7, nan_frac=0.01)
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=use_dask), oracle_cube(data, BENCH_WCS, use_dask=use_dask)
+    sc, oc = sc.with_mask(sc > -0.5), oc.with_mask(oc > -0.5)
+    k = 5 / 2.3548200450309493
+    got = sc.spectral_smooth(scb.Gaussian1DKernel(k)).unmasked_data[:]
+    want = oc.spectral_smooth(oconv.Gaussian1DKernel(k))._data
+    assert_maps_close(got, want, rtol=RTOL, what='fwhm5')
+
+
+def test_spectral_smooth_views_and_odd_widths():
+    import torch
+    scb = _kernels()
+    base = _random_cube((40, 9, 50), seed=9)
+    for sl in [(slice(None), slice(None), slice(0, 48)), (slice(3, 37), slice(1, 8), slice(2, 45)),
+               (slice(None), slice(None), slice(None))]:
+        dev = torch.from_numpy(base).cuda()[sl]
+        sc, oc = gpu_cube(dev, BENCH_WCS, use_dask=True), oracle_cube(base[sl], BENCH_WCS, use_dask=True)
+        got = sc.spectral_smooth(scb.Gaussian1DKernel(1.5)).unmasked_data[:]
+        want = oc.spectral_smooth(oconv.Gaussian1DKernel(1.5))._data
+        assert_maps_close(got, want, rtol=RTOL, what=str(sl))
+
+
+@pytest.mark.parametrize('kernel_path', ['tma', 'generic'])
+def test_smooth_then_moment_fused_matches_oracle(kernel_path, monkeypatch):
+    """config 3: spectral_smooth(Gaussian FWHM 5 ch) then moment0/1/2 on the dask class; the GPU path
+    never writes the smoothed cube."""
+    scb = _kernels()
+    monkeypatch.setenv('SC_SMOOTH_KERNEL', '2' if kernel_path == 'tma' else '1')
+    data = _random_cube((128, 6, 64), seed=17, nan_frac=0.01) + np.float32(4.0)     # positive weights
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=True), oracle_cube(data, BENCH_WCS, use_dask=True)
+    k = 5 / 2.3548200450309493
+    ssm, osm = sc.spectral_smooth(scb.Gaussian1DKernel(k)), oc.spectral_smooth(oconv.Gaussian1DKernel(k))
+    assert ssm._data_t is None                           # still lazy
+    for order in (0, 1, 2):
+        got = quiet(ssm.moment, order=order).value
+        want = quiet(osm.moment, order=order)[0]
+        assert_maps_close(got, want, rtol=RTOL, what='fused moment%d' % order)
+    assert ssm._data_t is None                           # the smoothed cube was never materialised
+    # and the materialised route gives the same maps
+    mat = sc.spectral_smooth(scb.Gaussian1DKernel(k), save_to_tmp_dir=True)
+    assert mat._data_t is not None
+    for order in (0, 1, 2):
+        assert_maps_close(quiet(mat.moment, order=order).value, quiet(ssm.moment, order=order).value,
+                          rtol=1e-9, atol=1e-9, what='materialised vs fused %d' % order)
+
+
+def test_smoothing_is_linear_and_preserves_constants_at_scale():
+    """Size-independent properties on a 512 x 256 x 2048 cube (1 GB): a constant cube stays constant
+    away from the spectral edges; smoothing 2x the data gives 2x the result exactly."""
+    import torch
+    from spectral_cube_b200.synth import synth_cube, benchmark_wcs
+    scb = _kernels()
+    nchan, ny, nx = 512, 256, 2048
+    w = benchmark_wcs(nchan, ny, nx)
+    k = scb.Gaussian1DKernel(5 / 2.3548200450309493)
+    const = scb.DaskSpectralCube(torch.full((nchan, ny, nx), 3.25, device='cuda'), w, unit='K')
+    out = const.spectral_smooth(k)._data
+    assert torch.allclose(out[8:-8], torch.full_like(out[8:-8], 3.25), rtol=1e-6, atol=0)
+    assert float(out[0].max()) < 3.25                    # zero-filled boundary tapers the edge channels
+    dev = synth_cube(nchan, ny, nx, nan_permille=1, border=4)
+    a = scb.DaskSpectralCube(dev, w, unit='K').spectral_smooth(k)._data
+    b = scb.DaskSpectralCube(dev * 2.0, w, unit='K').spectral_smooth(k)._data
+    assert torch.equal(torch.nan_to_num(b, nan=-1.0), torch.nan_to_num(a * 2.0, nan=-1.0))
+    # NaN-interpolation: an isolated NaN voxel is filled in, the all-NaN border stays NaN
+    assert bool(torch.isnan(a[:, 0, :]).all()) and not bool(torch.isnan(a[:, 10, 10:-10]).any())
+
+
+# ---- spatial smoothing: spectral_cube/tests/test_spectral_cube.py:2363-2421 ---------------------------
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_spatial_smooth_g2d(use_dask):
+    scb = _kernels()
+    cube = gpu_cube(G.adv_data(), G.ADV_WCS, use_dask=use_dask)
+    res = cube.spatial_smooth(scb.Gaussian2DKernel(3)).unmasked_data[:]
+    np.testing.assert_almost_equal(res[0], G.G2D_RESULT0)
+    np.testing.assert_almost_equal(res[2], G.G2D_RESULT2)
+
+
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_spatial_smooth_t2d(use_dask):
+    scb = _kernels()
+    cube = gpu_cube(G.adv_data(), G.ADV_WCS, use_dask=use_dask)
+    res = cube.spatial_smooth(scb.Tophat2DKernel(3)).unmasked_data[:]
+    np.testing.assert_almost_equal(res[0], G.T2D_RESULT0)
+    np.testing.assert_almost_equal(res[2], G.T2D_RESULT2)
+
+
+def test_spatial_smooth_preserves_unit_and_refuses_jybeam():
+    scb = _kernels()
+    cube = gpu_cube(G.adv_data(), G.ADV_WCS, unit='Jy/beam')
+    with pytest.raises(scb.BeamUnitsError, match="Jy/beam"):
+        cube.spatial_smooth(scb.Gaussian2DKernel(3))
+    out = cube.spatial_smooth(scb.Gaussian2DKernel(3), raise_error_jybm=False)
+    assert out.unit == 'Jy/beam'
+
+
+@pytest.mark.parametrize('use_dask', [False, True])
+@pytest.mark.parametrize('sigma', [0.5, 1.0, 8 / 2.3548200450309493, 4.0])
+def test_spatial_smooth_gaussian_matches_oracle(sigma, use_dask):
+    """Separable (marching) path incl. config 4's FWHM 8 px kernel (29 x 29)."""
+    scb = _kernels()
+    data = _random_cube((3, 70, 300), seed=int(sigma * 10), nan_frac=0.01)
+    data[1, 20:60, 100:160] = np.nan                     # a hole wider than the kernel: bot == 0 inside
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=use_dask), oracle_cube(data, BENCH_WCS, use_dask=use_dask)
+    got = sc.spatial_smooth(scb.Gaussian2DKernel(sigma)).unmasked_data[:]
+    want = oc.spatial_smooth(oconv.Gaussian2DKernel(sigma))._data
+    assert got.dtype == want.dtype
+    assert_maps_close(got, want, rtol=RTOL, what='sigma=%g' % sigma)
+
+
+def test_spatial_smooth_elliptical_and_nonseparable_match_oracle():
+    scb = _kernels()
+    data = _random_cube((2, 40, 64), seed=77, nan_frac=0.02)
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=True), oracle_cube(data, BENCH_WCS, use_dask=True)
+    for kg, ko in [(scb.Gaussian2DKernel(1.0, 2.0), oconv.Gaussian2DKernel(1.0, 2.0)),            # separable, hy != hx
+                   (scb.Gaussian2DKernel(1.0, 2.0, theta=0.5), oconv.Gaussian2DKernel(1.0, 2.0, theta=0.5)),
+                   (scb.Tophat2DKernel(3), oconv.Tophat2DKernel(3))]:
+        got = sc.spatial_smooth(kg).unmasked_data[:]
+        want = oc.spatial_smooth(ko)._data
+        assert_maps_close(got, want, rtol=RTOL, what=str(kg.shape))
+
+
+def test_spatial_smooth_under_mask_and_fill_value():
+    scb = _kernels()
+    data = _random_cube((2, 33, 140), seed=5, nan_frac=0.0)
+    for fill in (np.nan, 0.0):
+        sc, oc = gpu_cube(data, BENCH_WCS, use_dask=True), oracle_cube(data, BENCH_WCS, use_dask=True)
+        sc, oc = sc.with_mask(sc > 0.0).with_fill_value(fill), oc.with_mask(oc > 0.0).with_fill_value(fill)
+        got = sc.spatial_smooth(scb.Gaussian2DKernel(1.5)).unmasked_data[:]
+        want = oc.spatial_smooth(oconv.Gaussian2DKernel(1.5))._data
+        assert_maps_close(got, want, rtol=RTOL, atol=1e-7, what='fill=%r' % fill)
+
+
+def test_spatial_smooth_row_shards_with_halos_equal_the_whole_image():
+    """Row sharding: smoothing two row blocks with each other's filled edge rows as
+    halos reproduces the unsharded result bit for bit."""
+    import torch
+    from spectral_cube_b200 import _lib
+    scb = _kernels()
+    lib = _lib.load()
+    data = _random_cube((4, 64, 256), seed=31, nan_frac=0.01)
+    k = scb.Gaussian2DKernel(8 / 2.3548200450309493)
+    whole = gpu_cube(data, BENCH_WCS, use_dask=True)
+    ref = whole.spatial_smooth(k)._data
+    h = k.shape[0] // 2
+    top, bot = gpu_cube(data[:, :40], BENCH_WCS, use_dask=True), gpu_cube(data[:, 40:], BENCH_WCS, use_dask=True)
+
+    def pack(cube, row0, nrows):
+        out = torch.empty((cube.shape[0], nrows, cube.shape[2]), dtype=torch.float32, device='cuda')
+        desc, keep = cube._mask_desc()
+        d = cube._data
+        _lib.check(lib.sc_pack_filled_rows(d.data_ptr(), d.shape[0], d.shape[1], d.shape[2], d.stride(0), d.stride(1),
+                                           desc, float('nan'), row0, nrows, out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        return out
+    halo_for_top = pack(bot, 0, h)                       # the rows just below the top shard
+    halo_for_bot = pack(top, 40 - h, h)                  # the rows just above the bottom shard
+    a = top._run_spatial_smooth(k.array, _lib.F32, halo_top=None, halo_bot=halo_for_top, halo_rows=h)
+    b = bot._run_spatial_smooth(k.array, _lib.F32, halo_top=halo_for_bot, halo_bot=None, halo_rows=h)
+    got = torch.cat([a, b], dim=1)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
