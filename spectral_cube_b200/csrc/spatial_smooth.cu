@@ -155,18 +155,23 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
         mbar_wait(&sm.full[s], (b / SP_RS) & 1);
 
         // (1) in place: zero what the copy did not cover, apply mask/fill to the cube's own rows
-        for (int e = tid; e < SP_R * SP_W; e += SP_TX) {
-            const int r = e / SP_W, col = e - r * SP_W;
-            const int64_t y = yblk + r, x = x0 - SP_HP + col;
-            const bool in_x = x >= 0 && x < p.nx;
+#pragma unroll 1
+        for (int r = 0; r < SP_R; ++r) {
+            const int64_t y = yblk + r;                              // uniform
             const bool own = y >= 0 && y < p.ny;
             const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
-            float v = 0.0f;                                         // outside the image: a valid zero
-            if (in_x && (own || halo)) {
-                v = sm.raw[s][r][col];
-                if (own && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+            const bool need_mask = own && p.mask.mode != MODE_NONE;
+            const bool all_valid = (own || halo) && xl == x0 - SP_HP && xr == x0 + SP_TX + SP_HP;
+            if (all_valid && !need_mask) continue;                   // the copy filled the whole row as is
+            for (int col = tid; col < SP_W; col += SP_TX) {
+                const int64_t x = x0 - SP_HP + col;
+                float v = 0.0f;                                      // outside the image: a valid zero
+                if (x >= xl && x < xr && (own || halo)) {
+                    v = sm.raw[s][r][col];
+                    if (need_mask && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+                }
+                sm.raw[s][r][col] = v;
             }
-            sm.raw[s][r][col] = v;
         }
         compute_bar();
 
@@ -218,11 +223,19 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
             const int64_t yout = y_first + (int64_t)jb * SP_R;
             double w[NIN_Y];
             float bt[NIN_Y];
+            // ring slots of the 2 HB + 1 march-blocks this output block reads (block b - 2HB .. b)
+            int slot_of[2 * HB + 1];
+            {
+                int sl = (b - 2 * HB) % NB;
+#pragma unroll
+                for (int t = 0; t < 2 * HB + 1; ++t) { slot_of[t] = sl * SP_R; sl = (sl + 1 == NB) ? 0 : sl + 1; }
+            }
 #pragma unroll
             for (int i = 0; i < NIN_Y; ++i) {
-                // ring line of march-row jb*R - H + i
-                const int mr = jb * SP_R - H + i;
-                const int slot = ((mr / SP_R) % NB) * SP_R + (mr % SP_R);
+                // march-row jb*R - H + i, relative to the first row of block b - 2HB
+                constexpr int dummy = 0; (void)dummy;
+                const int rel = HB * SP_R - H + i;                   // compile-time
+                const int slot = slot_of[rel / SP_R] + (rel % SP_R);
                 w[i] = sm.top[slot][tid];
                 bt[i] = sm.bot[slot][tid];
             }
@@ -238,8 +251,7 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
                     bot = fmaf(p.tyf[k], bt[r + 2 * H - k], bot);
                 }
                 if (y < yb && x < p.nx) {
-                    const int mr = jb * SP_R + r;
-                    const float centre = sm.ctr[((mr / SP_R) % NB) * SP_R + (mr % SP_R)][tid];
+                    const float centre = sm.ctr[slot_of[HB] + r][tid];
                     double res;
                     if (bot == bot_full) res = top;
                     else if (bot == 0.0f) res = (double)centre;
@@ -302,6 +314,47 @@ direct2d_kernel(const __grid_constant__ DirectParams d) {
     else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
 }
 
+// flags[c] = 1 when no voxel of channel c is included by the mask: `_apply_spatial_function`
+// (spectral_cube.py:161-172) copies such a plane through instead of convolving it.  One CTA per
+// channel, early exit as soon as any thread sees an included voxel (the common case: first pass).
+__global__ void __launch_bounds__(256)
+plane_none_included_kernel(const __grid_constant__ SpatialParams p, uint8_t *flags) {
+    __shared__ int found;
+    const int64_t c = blockIdx.x;
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    const int64_t n = p.ny * p.nx;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        bool inc = false;
+        if (i < n) {
+            const int64_t y = i / p.nx, x = i - y * p.nx;
+            const float v = __ldg(p.in + c * p.stride_c + y * p.stride_y + x);
+            inc = mask_include_rt(p.mask, v, c, y, x);
+        }
+        if (__syncthreads_or(inc)) { if (threadIdx.x == 0) found = 1; break; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) flags[c] = found ? 0 : 1;
+}
+
+static int maybe_passthrough_flags(SpatialParams &p, int plane_passthrough, void *workspace, size_t workspace_bytes,
+                                   size_t offset, cudaStream_t s) {
+    p.passthrough = nullptr;
+    if (!plane_passthrough || p.mask.mode == MODE_NONE) return SC_OK;
+    const size_t need = offset + (size_t)p.nchan + 256;
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return SC_ERR_WORKSPACE;
+    }
+    uint8_t *flags = (uint8_t *)workspace + offset;
+    LaunchScope ls(0, s);
+    plane_none_included_kernel<<<(unsigned)p.nchan, 256, 0, s>>>(p, flags);
+    SC_CUDA(cudaGetLastError());
+    p.passthrough = flags;
+    return SC_OK;
+}
+
 template <int H, int OUT64>
 static cudaError_t launch_sep_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
     constexpr int HB = (H + SP_R - 1) / SP_R;
@@ -346,10 +399,7 @@ static int fill_common(SpatialParams &p, const float *in, void *out, int out_dty
     p.halo_top = halo_top; p.halo_bot = halo_bot; p.halo_rows = halo_rows;
     p.fill = (float)fill;
     p.passthrough = nullptr;
-    if (plane_passthrough && mask && mask->n_nodes > 0 && fill == fill) {
-        set_error("plane_passthrough with a finite fill value is not supported yet");
-        return SC_ERR_UNSUPPORTED;
-    }
+    (void)plane_passthrough;
     return build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
 }
 
@@ -380,6 +430,9 @@ extern "C" int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
     for (int k = 0; k < ntaps_x; ++k) sx += taps_x[k];
     SC_CHECK_ARG(fabs(sy * sx) > 1e-8, "The kernel can't be normalized, because its sum is close to zero.");
     cudaStream_t s = (cudaStream_t)stream;
+    rc = maybe_passthrough_flags(p, plane_passthrough, workspace, workspace_bytes,
+                                 (size_t)ntaps_y * ntaps_x * 8 + 512, s);
+    if (rc) return rc;
     const bool aligned = ((uintptr_t)in % 16 == 0) && stride_c % 4 == 0 && stride_y % 4 == 0 && nx % 4 == 0 &&
                          (!halo_top || (uintptr_t)halo_top % 16 == 0) && (!halo_bot || (uintptr_t)halo_bot % 16 == 0);
     const int choice = env_int("SC_SPATIAL_KERNEL", 0);          // 0 auto, 1 direct, 2 march
@@ -456,6 +509,8 @@ extern "C" int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
         return SC_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    rc = maybe_passthrough_flags(p, plane_passthrough, workspace, workspace_bytes, (size_t)nt * 8 + 512, s);
+    if (rc) return rc;
     double *host = (double *)malloc((size_t)nt * 8);
     for (int i = 0; i < nt; ++i) host[i] = taps[i] / sum;
     double *tdev = (double *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);

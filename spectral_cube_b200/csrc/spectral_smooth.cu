@@ -40,7 +40,7 @@ struct SmoothParams {
     float fill;
     double ksum;                             // sum of the normalised taps (~1)
     double taps[SM_MAX_TAPS];                // normalised, centred in a 2H+1 window, zero padded
-    const uint8_t *passthrough;              // (ny,nx) 1 = copy filled input through; may be NULL
+    int passthrough_spaxels;                 // numpy class: spaxels with nothing included are copied through
     // fused moments
     const double2 *tab;                      // {d, d^2} per channel
     double K, pix_size, m1_offset;
@@ -56,6 +56,31 @@ struct SmoothSmem {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
 };
+
+// float32 -> float64 through an opaque conversion so the NaN select stays on the float32 side
+__device__ __forceinline__ double cvt_f64(float v) {
+    double d;
+    asm("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(v));
+    return d;
+}
+
+// Rare path: some inputs of this output's window are NaN.  `wb` has bit j set when window entry j
+// (input o + j, tap 2H - j) is NaN.  Subtract the missing taps from the full kernel sum; if every
+// real tap is missing the denominator is exactly 0.
+template <int H>
+__device__ __noinline__ double smooth_bot_with_nans(const double *taps_sm, uint64_t wb, double ksum, int ntaps) {
+    double bot = ksum;
+    int nbad = 0;
+    const int h = ntaps >> 1;
+    while (wb) {
+        const int j = __ffsll((long long)wb) - 1;
+        wb &= wb - 1;
+        const int k = 2 * H - j;
+        bot -= taps_sm[k];
+        nbad += (k >= H - h && k <= H + h) ? 1 : 0;
+    }
+    return nbad >= ntaps ? 0.0 : bot;
+}
 
 // EPI 0: store float32, 1: store float64, 2: fused moments
 template <int H, int B, int STAGES, int MODE, int EPI>
@@ -105,14 +130,21 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     // ---------------- consumer warps ----------------
     const bool active = tid < width;
     const int64_t x = x0 + tid;
-    const bool pass = active && p.passthrough && p.passthrough[y * p.nx + x];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     int cnt = 0;
+    bool any_included = false;                                       // for the pass-through fix-up
+    char *outp = reinterpret_cast<char *>(p.out) + ((EPI == 1) ? 8 : 4) * (y * p.out_stride_y + x);
+    const int64_t out_step = ((EPI == 1) ? 8 : 4) * p.out_stride_c;
 
+    int sprev = STAGES - 1, scur = 0, snext = 1;                     // ring slots of blocks i-1, i, i+1
     mbar_wait(&sm.full[0], 0);
     for (int i = 0; i < nblk; ++i) {
         const int64_t c0 = (int64_t)i * B;
-        if (i + 1 < nblk) mbar_wait(&sm.full[(i + 1) % STAGES], ((i + 1) / STAGES) & 1);
+        if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
+        const float *pprev = &sm.data[sprev][B - H][tid];
+        const float *pcur = &sm.data[scur][0][tid];
+        const float *pnext = &sm.data[snext][0][tid];
+        const bool interior = (i >= 1) && (c0 + B + H <= p.nchan);   // every input channel exists
 
         // ---- gather the B + 2H inputs as float64, apply mask/fill, record NaN and include bits ----
         double w[NIN];
@@ -120,53 +152,41 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
         float centre_filled[B];
 #pragma unroll
         for (int q = 0; q < NIN; ++q) {
-            const int64_t cc = c0 - H + q;                         // uniform across the CTA
+            const int64_t cc = c0 - H + q;                           // uniform across the CTA
             float v = 0.0f;
-            bool valid_chan = cc >= 0 && cc < p.nchan;
-            if (valid_chan) {
-                const int blk = (q < H) ? i - 1 : (q < H + B ? i : i + 1);
-                const int row = (q < H) ? B - H + q : (q < H + B ? q - H : q - H - B);
-                v = sm.data[(blk + STAGES) % STAGES][row][tid];
+            if (interior || (cc >= 0 && cc < p.nchan)) {
+                v = (q < H) ? pprev[q * SM_TILE] : (q < H + B ? pcur[(q - H) * SM_TILE] : pnext[(q - H - B) * SM_TILE]);
                 const bool inc = mask_include<MODE>(p.mask, v, cc, y, x);
                 if (EPI == 2 && inc && v == v) incbits |= 1ull << q;
+                if (EPI != 2 && MODE != MODE_NONE && q >= H && q < H + B) any_included |= inc;
                 v = inc ? v : p.fill;
             }
             if (q >= H && q < H + B) centre_filled[q - H] = v;
             const bool isn = v != v;
             if (isn) nanbits |= 1ull << q;
-            w[q] = isn ? 0.0 : (double)v;
+            w[q] = cvt_f64(isn ? 0.0f : v);
         }
 
-        // ---- B outputs, n-tap chains with static register indices ----
+        // ---- B outputs, n-tap chains with static register indices; taps come from the constant bank ----
 #pragma unroll
         for (int o = 0; o < B; ++o) {
             const int64_t c = c0 + o;
-            if (c < p.nchan) {                                      // uniform
+            if (interior || c < p.nchan) {                           // uniform
                 double top = 0.0;
 #pragma unroll
-                for (int k = 0; k < NT; ++k) top = fma(sm.taps[k], w[o + 2 * H - k], top);   // out[c] += K[k] v[c + H - k]
+                for (int k = 0; k < NT; ++k) top = fma(p.taps[k], w[o + 2 * H - k], top);   // out[c] += K[k] v[c + H - k]
                 double res = top;
                 const uint64_t wb = (nanbits >> o) & ((1ull << NT) - 1ull);
                 if (wb != 0) {
-                    // window bit j <-> input w[o + j] <-> tap k = 2H - j
-                    double bot = p.ksum;
-                    int nbad = 0;
-                    uint64_t m = wb;
-                    while (m) {
-                        const int j = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const double kk = sm.taps[2 * H - j];
-                        bot -= kk;
-                        nbad += (2 * H - j >= H - (p.ntaps >> 1) && 2 * H - j <= H + (p.ntaps >> 1)) ? 1 : 0;
-                    }
-                    if (nbad >= p.ntaps) bot = 0.0;                 // nothing valid under the real taps
+                    const double bot = smooth_bot_with_nans<H>(sm.taps, wb, p.ksum, p.ntaps);
                     res = (bot == 0.0) ? (double)centre_filled[o] : top / bot;
                 }
-                if (pass) res = (double)centre_filled[o];
                 if (EPI == 0) {
-                    if (active) reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
+                    if (active) *reinterpret_cast<float *>(outp) = (float)res;
+                    outp += out_step;
                 } else if (EPI == 1) {
-                    if (active) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
+                    if (active) *reinterpret_cast<double *>(outp) = res;
+                    outp += out_step;
                 } else {
                     // fused moments: the smoothed value enters as the materialised dtype would hold it,
                     // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
@@ -183,7 +203,20 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
             }
         }
         __syncwarp();
-        if (i >= 1 && lane == 0) mbar_arrive(&sm.empty[(i - 1) % STAGES]);
+        if (i >= 1 && lane == 0) mbar_arrive(&sm.empty[sprev]);
+        sprev = scur; scur = snext; snext = (snext + 1 == STAGES) ? 0 : snext + 1;
+    }
+    if (EPI != 2 && MODE != MODE_NONE && p.passthrough_spaxels && active && !any_included) {
+        // `_apply_spectral_function` (spectral_cube.py:147-158): a spaxel with nothing included is
+        // copied through (= the fill value everywhere).  Away from the spectral edges the convolution
+        // already produced that; the first/last h channels saw valid zero padding and must be redone.
+        const int h = p.ntaps >> 1;
+        char *o0 = reinterpret_cast<char *>(p.out) + ((EPI == 1) ? 8 : 4) * (y * p.out_stride_y + x);
+        for (int64_t c = 0; c < p.nchan; ++c) {
+            if (c >= h && c < p.nchan - h) { c = p.nchan - h - 1; continue; }
+            if (EPI == 0) *reinterpret_cast<float *>(o0 + c * out_step) = p.fill;
+            else          *reinterpret_cast<double *>(o0 + c * out_step) = (double)p.fill;
+        }
     }
     if (EPI == 2 && active) {
         const int64_t o = y * p.nx + x;
@@ -204,9 +237,9 @@ smooth_generic_kernel(const __grid_constant__ SmoothParams p, const double *__re
     const int64_t y = g / p.nx, x = g - y * p.nx;
     const int h = ntaps >> 1;
     const float *src = p.in + y * p.stride_y + x;
-    const bool pass = p.passthrough && p.passthrough[g];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     int cnt = 0;
+    bool any_included = false;
     for (int64_t c = 0; c < p.nchan; ++c) {
         double top = 0.0, bot = 0.0;
         float centre = 0.0f;
@@ -217,14 +250,13 @@ smooth_generic_kernel(const __grid_constant__ SmoothParams p, const double *__re
             if (cc >= 0 && cc < p.nchan) {
                 v = __ldg(src + cc * p.stride_c);
                 const bool inc = mask_include<MODE>(p.mask, v, cc, y, x);
-                if (k == h) centre_inc = inc && v == v;
+                if (k == h) { centre_inc = inc && v == v; any_included |= inc; }
                 v = inc ? v : p.fill;
             }
             if (k == h) centre = v;
             if (v == v) { top = fma(taps[k], (double)v, top); bot += taps[k]; }
         }
         double res = (bot == 0.0) ? (double)centre : top / bot;
-        if (pass) res = (double)centre;
         if (EPI == 0)      reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
         else if (EPI == 1) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
         else {
@@ -233,6 +265,12 @@ smooth_generic_kernel(const __grid_constant__ SmoothParams p, const double *__re
                 const double2 t = __ldg(p.tab + c);
                 s0 += sv; s1 = fma(sv, t.x, s1); s2 = fma(sv, t.y, s2); cnt += 1;
             }
+        }
+    }
+    if (EPI != 2 && MODE != MODE_NONE && p.passthrough_spaxels && !any_included) {
+        for (int64_t c = 0; c < p.nchan; ++c) {
+            if (EPI == 0) reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = p.fill;
+            else          reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (double)p.fill;
         }
     }
     if (EPI == 2) {
@@ -367,13 +405,8 @@ extern "C" int sc_spectral_smooth(const float *in, void *out, int out_dtype,
     p.in = in; p.out = out; p.nchan = nchan; p.ny = ny; p.nx = nx;
     p.stride_c = stride_c; p.stride_y = stride_y; p.out_stride_c = out_stride_c; p.out_stride_y = out_stride_y;
     p.fill = (float)fill;
-    p.passthrough = nullptr;
-    // `_apply_spectral_function` copies a spaxel with nothing included (spectral_cube.py:155-158); that
-    // only differs from convolving it when the fill value is finite.
-    if (spaxel_passthrough && mask && mask->n_nodes > 0 && fill == fill) {
-        set_error("spaxel_passthrough with a finite fill value is not supported yet");
-        return SC_ERR_UNSUPPORTED;
-    }
+    // `_apply_spectral_function` copies a spaxel with nothing included (spectral_cube.py:155-158)
+    p.passthrough_spaxels = spaxel_passthrough ? 1 : 0;
     if (out_dtype == SC_F32) return run_smooth<0>(p, mask, taps, ntaps, workspace, workspace_bytes, 0, s, SC_OP_SPECTRAL_SMOOTH);
     return run_smooth<1>(p, mask, taps, ntaps, workspace, workspace_bytes, 0, s, SC_OP_SPECTRAL_SMOOTH);
 }

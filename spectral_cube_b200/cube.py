@@ -296,7 +296,8 @@ class BaseSpectralCube(object):
     def _get_workspace(self, nbytes):
         torch = _torch()
         if self._workspace is None or self._workspace.numel() < nbytes:
-            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self._data.device)
+            dev = self._data_t.device if self._data_t is not None else self._pending.source._data.device
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         return self._workspace
 
     # -- smoothing (spectral_cube.py:3186-3222, 2808-2842; dask_spectral_cube.py:880-917, 962-993) ----
@@ -330,7 +331,8 @@ class BaseSpectralCube(object):
         tarr, tptr = _lib.as_double_array(taps)
         _lib.check(lib.sc_spectral_smooth(
             src.data_ptr(), out.data_ptr(), out_dtype, nchan, ny, nx, src.stride(0), src.stride(1),
-            out.stride(0), out.stride(1), desc, float(self._smooth_fill()), tptr, len(taps), 0,
+            out.stride(0), out.stride(1), desc, float(self._smooth_fill()), tptr, len(taps),
+            0 if self._mirrors_dask else 1,      # numpy class: _apply_spectral_function pass-through (:147-158)
             ws.data_ptr(), ws.numel(), _stream()))
         return out
 
@@ -375,14 +377,15 @@ class BaseSpectralCube(object):
         hb = halo_bot.data_ptr() if halo_bot is not None else None
         common = (src.data_ptr(), out.data_ptr(), out_dtype, nchan, ny, nx, src.stride(0), src.stride(1),
                   out.stride(0), out.stride(1), desc, float(self._fill_value))
+        passthrough = 0 if self._mirrors_dask else 1     # _apply_spatial_function (:161-172)
         sep = self._separable_factors(k2d)
         if sep is not None:
             (ya, yp), (xa, xp) = _lib.as_double_array(sep[0]), _lib.as_double_array(sep[1])
-            _lib.check(lib.sc_spatial_smooth_sep(*common, yp, len(ya), xp, len(xa), ht, hb, int(halo_rows), 0,
+            _lib.check(lib.sc_spatial_smooth_sep(*common, yp, len(ya), xp, len(xa), ht, hb, int(halo_rows), passthrough,
                                                  ws.data_ptr(), ws.numel(), _stream()))
         else:
             ka, kp = _lib.as_double_array(k2d.ravel())
-            _lib.check(lib.sc_spatial_smooth_2d(*common, kp, k2d.shape[0], k2d.shape[1], ht, hb, int(halo_rows), 0,
+            _lib.check(lib.sc_spatial_smooth_2d(*common, kp, k2d.shape[0], k2d.shape[1], ht, hb, int(halo_rows), passthrough,
                                                 ws.data_ptr(), ws.numel(), _stream()))
         return out
 
