@@ -1,0 +1,220 @@
+// reproject.cu -- spatial reprojection of every channel onto a new celestial WCS.
+//
+// Replaces `reproject.reproject_interp((data, header), wcs_out, shape_out=..., order=...)` as
+// called at spectral_cube.py:2726-2732.  Two kernels:
+//
+//  * wcs_pixel_map_kernel: for every output pixel, output-WCS pixel -> world and input-WCS
+//    world -> pixel in float64 (FITS WCS paper I linear part, paper II TAN/SIN zenithal
+//    projections and the native<->celestial rotation).  The transform is carried through unit
+//    vectors, so no inverse trigonometric function is evaluated.  The spectral axis is
+//    uncorrelated with the celestial axes (enforced by the reference, spectral_cube.py:1513-1515),
+//    so the two coordinate planes are computed once and shared by all channels.
+//
+//  * reproject_kernel: a thread owns one output pixel (CTA = 32 x 8 output tile, so the input
+//    footprint of a CTA is compact and neighbouring tiles share lines in L1/L2), derives its
+//    four neighbours and weights once, then walks the channels with four independent gathers
+//    in flight per step.  Semantics follow reproject's `map_coordinates(order=1,
+//    mode='constant', cval=nan)` on an edge-padded image: samples up to half a pixel outside
+//    the outermost pixel centres are kept, everything further out is NaN, and a NaN neighbour
+//    poisons the sample even at zero weight.  footprint = ~isnan(result).
+#include "common.cuh"
+
+namespace scb {
+
+int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
+
+struct WcsCel {              // celestial part of a FITS WCS
+    double crpix1, crpix2, crval1, crval2, m11, m12, m21, m22, lonpole;
+    int sin_proj;            // 0 TAN, 1 SIN
+    double i11, i12, i21, i22;   // inverse of m
+};
+
+__global__ void __launch_bounds__(256)
+wcs_pixel_map_kernel(WcsCel wo, WcsCel wi, int64_t ny, int64_t nx, double *yin, double *xin) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ny * nx) return;
+    const int64_t py = g / nx, px = g - py * nx;
+    const double D2R = 0.017453292519943295, R2D = 57.29577951308232;
+    // ---- output pixel -> native unit vector (paper I eq. 1; paper II eq. 54 / 59) ----
+    const double dx = (double)px + 1.0 - wo.crpix1, dy = (double)py + 1.0 - wo.crpix2;
+    const double xr = (wo.m11 * dx + wo.m12 * dy) * D2R, yr = (wo.m21 * dx + wo.m22 * dy) * D2R;
+    const double r2 = xr * xr + yr * yr;
+    double st, ctsp, ctcp;             // sin(theta), cos(theta) sin(phi), cos(theta) cos(phi)
+    bool bad = false;
+    if (!wo.sin_proj) { st = 1.0 / sqrt(1.0 + r2); ctsp = xr * st; ctcp = -yr * st; }
+    else { bad = r2 > 1.0; st = sqrt(fmax(1.0 - r2, 0.0)); ctsp = xr; ctcp = -yr; }
+    // ---- native -> celestial (paper II eq. 2), kept as a unit vector about alpha_p ----
+    double sp, cp, sd, cd;
+    sincos(wo.lonpole * D2R, &sp, &cp);
+    sincos(wo.crval2 * D2R, &sd, &cd);
+    const double ct_c = ctcp * cp + ctsp * sp;        // cos(theta) cos(phi - phi_p)
+    const double ct_s = ctsp * cp - ctcp * sp;        // cos(theta) sin(phi - phi_p)
+    const double cz = st * sd + ct_c * cd;            // sin(delta)
+    const double cx = st * cd - ct_c * sd;            // cos(delta) cos(alpha - alpha_p)
+    const double cy = -ct_s;                          // cos(delta) sin(alpha - alpha_p)
+    // ---- shift the longitude origin to the input WCS's alpha_p ----
+    double sa, ca;
+    sincos((wo.crval1 - wi.crval1) * D2R, &sa, &ca);
+    const double ex = cx * ca - cy * sa;              // cos(delta) cos(alpha - alpha_p')
+    const double ey = cx * sa + cy * ca;              // cos(delta) sin(alpha - alpha_p')
+    // ---- celestial -> native of the input WCS (paper II eq. 5) ----
+    double sdi, cdi, spi, cpi;
+    sincos(wi.crval2 * D2R, &sdi, &cdi);
+    sincos(wi.lonpole * D2R, &spi, &cpi);
+    const double st_i = cz * sdi + ex * cdi;          // sin(theta)
+    const double ctc_i = cz * cdi - ex * sdi;         // cos(theta) cos(phi - phi_p)
+    const double cts_i = -ey;                         // cos(theta) sin(phi - phi_p)
+    const double ctsp_i = cts_i * cpi + ctc_i * spi;  // cos(theta) sin(phi)
+    const double ctcp_i = ctc_i * cpi - cts_i * spi;  // cos(theta) cos(phi)
+    double xi, yi;
+    if (!wi.sin_proj) { bad |= st_i <= 0.0; xi = ctsp_i / st_i * R2D; yi = -ctcp_i / st_i * R2D; }
+    else { bad |= st_i < 0.0; xi = ctsp_i * R2D; yi = -ctcp_i * R2D; }
+    const double qx = wi.i11 * xi + wi.i12 * yi + wi.crpix1 - 1.0;
+    const double qy = wi.i21 * xi + wi.i22 * yi + wi.crpix2 - 1.0;
+    xin[g] = bad ? nan64() : qx;
+    yin[g] = bad ? nan64() : qy;
+}
+
+struct ReprojParams {
+    const float *in;
+    void *out;
+    uint8_t *footprint;
+    int64_t nchan, ny_in, nx_in, stride_c, stride_y, ny_out, nx_out;
+    const double *yin, *xin;
+    float fill;
+    int order;
+    int chan_per_cta;
+    DevMask mask;
+};
+
+template <int MODE>
+__device__ __forceinline__ float load_filled(const ReprojParams &p, const float *plane, int64_t c, int64_t y, int64_t x) {
+    const float v = __ldg(plane + y * p.stride_y + x);
+    if (MODE == MODE_NONE) return v;
+    return mask_include<MODE>(p.mask, v, c, y, x) ? v : p.fill;
+}
+
+template <int MODE, int OUT64>
+__global__ void __launch_bounds__(256)
+reproject_kernel(const __grid_constant__ ReprojParams p) {
+    const int64_t xo = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const int64_t yo = (int64_t)blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (xo >= p.nx_out || yo >= p.ny_out) return;
+    const int64_t o = yo * p.nx_out + xo;
+    const double ys = p.yin[o], xs = p.xin[o];
+    const bool outside = !(ys >= -0.5 && ys <= (double)p.ny_in - 0.5 && xs >= -0.5 && xs <= (double)p.nx_in - 0.5);
+    int64_t r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+    double wy0 = 0, wy1 = 0, wx0 = 0, wx1 = 0;
+    if (!outside) {
+        if (p.order == 0) {
+            // nearest neighbour: scipy order 0 rounds half up
+            r0 = r1 = min(max((int64_t)floor(ys + 0.5), (int64_t)0), p.ny_in - 1);
+            c0 = c1 = min(max((int64_t)floor(xs + 0.5), (int64_t)0), p.nx_in - 1);
+            wy0 = 1.0; wx0 = 1.0;
+        } else {
+            const double fy = floor(ys), fx = floor(xs);
+            wy1 = ys - fy; wy0 = 1.0 - wy1;
+            wx1 = xs - fx; wx0 = 1.0 - wx1;
+            // edge-replicated padding: neighbours clamp to the image
+            r0 = min(max((int64_t)fy, (int64_t)0), p.ny_in - 1);
+            r1 = min(max((int64_t)fy + 1, (int64_t)0), p.ny_in - 1);
+            c0 = min(max((int64_t)fx, (int64_t)0), p.nx_in - 1);
+            c1 = min(max((int64_t)fx + 1, (int64_t)0), p.nx_in - 1);
+        }
+    }
+    const double w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+    const int64_t cbeg = (int64_t)blockIdx.z * p.chan_per_cta;
+    const int64_t cend = min(p.nchan, cbeg + p.chan_per_cta);
+    const int64_t plane_out = p.ny_out * p.nx_out;
+#pragma unroll 4
+    for (int64_t c = cbeg; c < cend; ++c) {
+        double res = nan64();
+        if (!outside) {
+            const float *plane = p.in + c * p.stride_c;
+            if (p.order == 0) {
+                res = (double)load_filled<MODE>(p, plane, c, r0, c0);
+            } else {
+                const double v00 = (double)load_filled<MODE>(p, plane, c, r0, c0);
+                const double v01 = (double)load_filled<MODE>(p, plane, c, r0, c1);
+                const double v10 = (double)load_filled<MODE>(p, plane, c, r1, c0);
+                const double v11 = (double)load_filled<MODE>(p, plane, c, r1, c1);
+                res = w00 * v00;
+                res = fma(w01, v01, res);
+                res = fma(w10, v10, res);
+                res = fma(w11, v11, res);
+            }
+        }
+        if (OUT64) reinterpret_cast<double *>(p.out)[c * plane_out + o] = res;
+        else       reinterpret_cast<float *>(p.out)[c * plane_out + o] = (float)res;
+        if (p.footprint) p.footprint[c * plane_out + o] = (res == res) ? 1 : 0;
+    }
+}
+
+static bool unpack_wcs(const double *w, WcsCel *out) {
+    out->crpix1 = w[0]; out->crpix2 = w[1]; out->crval1 = w[2]; out->crval2 = w[3];
+    out->m11 = w[4]; out->m12 = w[5]; out->m21 = w[6]; out->m22 = w[7];
+    out->lonpole = w[8]; out->sin_proj = w[9] != 0.0 ? 1 : 0;
+    const double det = out->m11 * out->m22 - out->m12 * out->m21;
+    if (det == 0.0 || det != det) return false;
+    out->i11 = out->m22 / det; out->i12 = -out->m12 / det; out->i21 = -out->m21 / det; out->i22 = out->m11 / det;
+    return true;
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int sc_wcs_pixel_map(const double *wcs_out, const double *wcs_in,
+                                int64_t ny_out, int64_t nx_out, double *yin, double *xin, void *stream) {
+    SC_CHECK_ARG(wcs_out && wcs_in && yin && xin, "NULL argument");
+    SC_CHECK_ARG(ny_out > 0 && nx_out > 0, "bad output shape");
+    WcsCel wo, wi;
+    SC_CHECK_ARG(unpack_wcs(wcs_out, &wo) && unpack_wcs(wcs_in, &wi), "singular pixel scale matrix");
+    cudaStream_t s = (cudaStream_t)stream;
+    LaunchScope ls(0, s);
+    wcs_pixel_map_kernel<<<(unsigned)cdiv(ny_out * nx_out, 256), 256, 0, s>>>(wo, wi, ny_out, nx_out, yin, xin);
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+}
+
+extern "C" int sc_reproject(const float *in, void *out, int out_dtype, uint8_t *footprint,
+                            int64_t nchan, int64_t ny_in, int64_t nx_in,
+                            int64_t stride_c, int64_t stride_y,
+                            int64_t ny_out, int64_t nx_out,
+                            const sc_mask_desc *mask, double fill,
+                            const double *yin, const double *xin, int order, void *stream) {
+    int rc = check_cube_args(in, nchan, ny_in, nx_in, stride_c, stride_y);
+    if (rc) return rc;
+    SC_CHECK_ARG(out && yin && xin, "out / yin / xin must not be NULL");
+    SC_CHECK_ARG(ny_out > 0 && nx_out > 0, "bad output shape");
+    SC_CHECK_ARG(out_dtype == SC_F32 || out_dtype == SC_F64, "out_dtype must be SC_F32 or SC_F64");
+    SC_CHECK_ARG(order == 0 || order == 1, "only nearest-neighbor (0) and bilinear (1) are implemented");
+    ReprojParams p{};
+    p.in = in; p.out = out; p.footprint = footprint;
+    p.nchan = nchan; p.ny_in = ny_in; p.nx_in = nx_in; p.stride_c = stride_c; p.stride_y = stride_y;
+    p.ny_out = ny_out; p.nx_out = nx_out; p.yin = yin; p.xin = xin; p.fill = (float)fill; p.order = order;
+    rc = build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
+    if (rc) return rc;
+    // channel chunks: enough CTAs for the chip, long enough runs to amortise the weight set-up
+    const int64_t tiles = cdiv(nx_out, 32) * cdiv(ny_out, 8);
+    int64_t zchunks = 1;
+    while (tiles * zchunks < 148 * 16 && zchunks * 2 <= nchan && nchan / (zchunks * 2) >= 8) zchunks *= 2;
+    if (zchunks > 65535) zchunks = 65535;
+    p.chan_per_cta = (int)cdiv(nchan, zchunks);
+    dim3 grid((unsigned)cdiv(nx_out, 32), (unsigned)cdiv(ny_out, 8), (unsigned)cdiv(nchan, p.chan_per_cta));
+    SC_CHECK_ARG(grid.y <= 65535, "output image too tall for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    LaunchScope ls(SC_OP_REPROJECT, s);
+    const int m = p.mask.mode;
+    if (out_dtype == SC_F64) {
+        if (m == MODE_NONE) reproject_kernel<MODE_NONE, 1><<<grid, 256, 0, s>>>(p);
+        else if (m == MODE_INTERVAL) reproject_kernel<MODE_INTERVAL, 1><<<grid, 256, 0, s>>>(p);
+        else reproject_kernel<MODE_GENERIC, 1><<<grid, 256, 0, s>>>(p);
+    } else {
+        if (m == MODE_NONE) reproject_kernel<MODE_NONE, 0><<<grid, 256, 0, s>>>(p);
+        else if (m == MODE_INTERVAL) reproject_kernel<MODE_INTERVAL, 0><<<grid, 256, 0, s>>>(p);
+        else reproject_kernel<MODE_GENERIC, 0><<<grid, 256, 0, s>>>(p);
+    }
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+}

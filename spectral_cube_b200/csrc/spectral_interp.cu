@@ -1,0 +1,196 @@
+// spectral_interp.cu -- per-spaxel 1-D linear resampling of the spectral axis.
+//
+// Replaces the per-spaxel `np.interp(grid, inaxis, spectrum, left, right)` loop of the numpy
+// class (spectral_cube.py:3298-3315) and the per-block `scipy.interpolate.interp1d` call of
+// the dask class (dask_spectral_cube.py:1342-1349).
+//
+// The host turns the output grid into a sorted look-up table (one entry per output channel:
+// bracketing input channel, knot coordinates, classification).  A thread owns one spaxel and
+// streams its spectrum ONCE in ascending-axis order, keeping the previous sample in a register;
+// every LUT entry is emitted when the highest input channel it needs arrives, so the inputs are
+// read exactly once (4 B/voxel) whatever the grid, warps read/write 128 contiguous bytes per
+// channel, and the per-spaxel "anything included?" flag the numpy class needs
+// (spectral_cube.py:3299-3313) falls out of the same pass.  Arithmetic is float64 and follows
+// numpy's / scipy's formulas term by term (see interp_numpy / interp_scipy below).
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace scb {
+
+int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
+
+enum { IK_INTERIOR = 0, IK_KNOT = 1, IK_LEFT = 2, IK_RIGHT = 3 };
+
+struct InterpEntry {          // 32 bytes
+    int32_t need;             // highest ascending-order input channel this entry needs
+    int32_t kind;
+    double x, xlo, xhi;
+};
+
+struct InterpParams {
+    const float *in;
+    void *out;
+    uint8_t *out_mask;
+    int64_t nchan, ny, nx, stride_c, stride_y, nchan_out;
+    const InterpEntry *lut;   // device, nchan_out entries sorted by x
+    float fill;
+    int has_fill_value;
+    double fill_value;
+    int in_reversed, out_reversed, mode;
+    DevMask mask;
+};
+
+// numpy/_core/src/multiarray/compiled_base.c (arr_interp): interior sample between two knots
+__device__ __forceinline__ double interp_numpy(double x, double xlo, double xhi, double f0, double f1) {
+    const double slope = (f1 - f0) / (xhi - xlo);
+    double r = slope * (x - xlo) + f0;
+    if (r != r) {
+        r = slope * (x - xhi) + f1;
+        if (r != r && f0 == f1) r = f0;
+    }
+    return r;
+}
+
+// scipy/interpolate/_interpolate.py (interp1d._call_linear)
+__device__ __forceinline__ double interp_scipy(double x, double xlo, double xhi, double f0, double f1) {
+    const double slope = (f1 - f0) / (xhi - xlo);
+    return slope * (x - xlo) + f0;
+}
+
+template <int MODE, int OUT64>
+__global__ void __launch_bounds__(128)
+spectral_interp_kernel(const __grid_constant__ InterpParams p) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ny * p.nx) return;
+    const int64_t y = g / p.nx, x = g - y * p.nx;
+    const float *src = p.in + y * p.stride_y + x;
+    const int64_t plane_out = p.ny * p.nx;
+    const int64_t obase = y * p.nx + x;
+
+    float prev = 0.0f, cur = 0.0f;          // filled values of ascending channels i-1, i
+    bool mprev = false, mcur = false;       // their include flags
+    bool any_included = false;
+    int64_t jj = 0;
+    for (int64_t i = 0; i < p.nchan; ++i) {
+        const int64_t ch = p.in_reversed ? p.nchan - 1 - i : i;
+        const float raw = ldg_stream1(src + ch * p.stride_c);
+        prev = cur; mprev = mcur;
+        mcur = mask_include<MODE>(p.mask, raw, ch, y, x);
+        cur = mcur ? raw : p.fill;
+        any_included |= mcur;
+        while (jj < p.nchan_out) {
+            const InterpEntry e = p.lut[jj];
+            if (e.need != (int32_t)i) break;
+            double r;
+            bool m;
+            if (p.mode == 0) {
+                if (e.kind == IK_INTERIOR) { r = interp_numpy(e.x, e.xlo, e.xhi, (double)prev, (double)cur); m = mprev | mcur; }
+                else if (e.kind == IK_KNOT) { r = (double)cur; m = mcur; }
+                else { r = p.has_fill_value ? p.fill_value : (double)cur; m = mcur; }       // left / right of the axis
+            } else {
+                if (e.kind == IK_LEFT || e.kind == IK_RIGHT) r = p.has_fill_value ? p.fill_value : nan64();
+                else r = interp_scipy(e.x, e.xlo, e.xhi, (double)prev, (double)cur);
+                m = r == r;
+            }
+            const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
+            // dask: the mask is taken BEFORE the output is flipped back (dask_spectral_cube.py:1364-1367)
+            const int64_t jm = (p.mode == 1) ? jj : jo;
+            if (OUT64) reinterpret_cast<double *>(p.out)[jo * plane_out + obase] = r;
+            else       reinterpret_cast<float *>(p.out)[jo * plane_out + obase] = (float)r;
+            if (p.out_mask) p.out_mask[jm * plane_out + obase] = m ? 1 : 0;
+            ++jj;
+        }
+    }
+    if (p.mode == 0 && !any_included && (p.fill == p.fill || p.has_fill_value)) {
+        // nothing included in this spaxel: data NaN, mask False (spectral_cube.py:3311-3313); only
+        // differs from what was emitted when a finite fill / fill_value was in play
+        for (int64_t j = 0; j < p.nchan_out; ++j) {
+            if (OUT64) reinterpret_cast<double *>(p.out)[j * plane_out + obase] = nan64();
+            else       reinterpret_cast<float *>(p.out)[j * plane_out + obase] = nan32();
+            if (p.out_mask) p.out_mask[j * plane_out + obase] = 0;
+        }
+    }
+}
+
+template <int OUT64>
+static cudaError_t launch_interp(const InterpParams &p, cudaStream_t s) {
+    const unsigned grid = (unsigned)cdiv(p.ny * p.nx, 128);
+    switch (p.mask.mode) {
+        case MODE_NONE:     spectral_interp_kernel<MODE_NONE, OUT64><<<grid, 128, 0, s>>>(p); break;
+        case MODE_INTERVAL: spectral_interp_kernel<MODE_INTERVAL, OUT64><<<grid, 128, 0, s>>>(p); break;
+        default:            spectral_interp_kernel<MODE_GENERIC, OUT64><<<grid, 128, 0, s>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uint8_t *out_mask,
+                                  int64_t nchan, int64_t ny, int64_t nx,
+                                  int64_t stride_c, int64_t stride_y,
+                                  int64_t nchan_out,
+                                  const sc_mask_desc *mask, double fill,
+                                  const double *in_axis, const double *grid,
+                                  int has_fill_value, double fill_value,
+                                  int in_reversed, int out_reversed, int mode,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_cube_args(in, nchan, ny, nx, stride_c, stride_y);
+    if (rc) return rc;
+    SC_CHECK_ARG(out != nullptr, "out is NULL");
+    SC_CHECK_ARG(out_dtype == SC_F32 || out_dtype == SC_F64, "out_dtype must be SC_F32 or SC_F64");
+    SC_CHECK_ARG(nchan_out > 0 && nchan_out < ((int64_t)1 << 31) && nchan < ((int64_t)1 << 31), "bad channel counts");
+    SC_CHECK_ARG(in_axis && grid, "in_axis / grid must not be NULL");
+    SC_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (numpy class) or 1 (dask class)");
+    SC_CHECK_ARG(nchan >= 2, "need at least two input channels");
+    for (int64_t i = 1; i < nchan; ++i)
+        SC_CHECK_ARG(in_axis[i] > in_axis[i - 1], "in_axis must be strictly ascending (flip it and set in_reversed)");
+    for (int64_t j = 1; j < nchan_out; ++j)
+        SC_CHECK_ARG(grid[j] > grid[j - 1], "grid must be strictly ascending (flip it and set out_reversed)");
+    const size_t need = (size_t)nchan_out * sizeof(InterpEntry) + 256;
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return SC_ERR_WORKSPACE;
+    }
+    // ---- host: classify every output sample (numpy: binary search with x == xp[j] and x == xp[-1]
+    //      special cases; scipy: searchsorted(left) clipped to [1, n-1]) ----
+    std::vector<InterpEntry> lut((size_t)nchan_out);
+    const double x_first = in_axis[0], x_last = in_axis[nchan - 1];
+    for (int64_t j = 0; j < nchan_out; ++j) {
+        const double xv = grid[j];
+        InterpEntry e{};
+        e.x = xv;
+        if (xv < x_first) { e.kind = IK_LEFT; e.need = 0; }
+        else if (xv > x_last) { e.kind = IK_RIGHT; e.need = (int32_t)(nchan - 1); }
+        else if (mode == 0) {
+            // largest k with in_axis[k] <= xv
+            const int64_t k = (std::upper_bound(in_axis, in_axis + nchan, xv) - in_axis) - 1;
+            if (k == nchan - 1 || in_axis[k] == xv) { e.kind = IK_KNOT; e.need = (int32_t)k; }
+            else { e.kind = IK_INTERIOR; e.need = (int32_t)(k + 1); e.xlo = in_axis[k]; e.xhi = in_axis[k + 1]; }
+        } else {
+            int64_t hi = std::lower_bound(in_axis, in_axis + nchan, xv) - in_axis;    // searchsorted(left)
+            if (hi < 1) hi = 1;
+            if (hi > nchan - 1) hi = nchan - 1;
+            e.kind = IK_INTERIOR; e.need = (int32_t)hi; e.xlo = in_axis[hi - 1]; e.xhi = in_axis[hi];
+        }
+        lut[(size_t)j] = e;
+    }
+    // `need` must be non-decreasing for the single streaming pass (it is: grid and axis are sorted;
+    // LEFT entries need channel 0 and precede everything, RIGHT entries need the last channel)
+    cudaStream_t s = (cudaStream_t)stream;
+    InterpEntry *lut_dev = (InterpEntry *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    SC_CUDA(cudaMemcpyAsync(lut_dev, lut.data(), (size_t)nchan_out * sizeof(InterpEntry), cudaMemcpyHostToDevice, s));
+    InterpParams p{};
+    p.in = in; p.out = out; p.out_mask = out_mask;
+    p.nchan = nchan; p.ny = ny; p.nx = nx; p.stride_c = stride_c; p.stride_y = stride_y; p.nchan_out = nchan_out;
+    p.lut = lut_dev; p.fill = (float)fill; p.has_fill_value = has_fill_value; p.fill_value = fill_value;
+    p.in_reversed = in_reversed; p.out_reversed = out_reversed; p.mode = mode;
+    rc = build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
+    if (rc) return rc;
+    LaunchScope ls(SC_OP_SPECTRAL_INTERP, s);
+    cudaError_t e = out_dtype == SC_F64 ? launch_interp<1>(p, s) : launch_interp<0>(p, s);
+    if (e != cudaSuccess) return cuda_fail(e, "spectral_interp_kernel launch");
+    return SC_OK;
+}

@@ -69,9 +69,22 @@ __device__ __forceinline__ double cvt_f64(float v) {
 // real tap is missing the denominator is exactly 0.
 template <int H>
 __device__ __noinline__ double smooth_bot_with_nans(const double *taps_sm, uint64_t wb, double ksum, int ntaps) {
+    constexpr uint64_t FULL = (1ull << (2 * H + 1)) - 1ull;
+    if (wb == FULL) return 0.0;                              // whole window missing (blank spectra)
+    const int h = ntaps >> 1;
+    if (__popcll(wb) > H) {
+        // mostly missing: add up what is there (taps outside the real kernel are zero)
+        double bot = 0.0;
+        uint64_t good = ~wb & FULL;
+        while (good) {
+            const int j = __ffsll((long long)good) - 1;
+            good &= good - 1;
+            bot += taps_sm[2 * H - j];
+        }
+        return bot;
+    }
     double bot = ksum;
     int nbad = 0;
-    const int h = ntaps >> 1;
     while (wb) {
         const int j = __ffsll((long long)wb) - 1;
         wb &= wb - 1;
@@ -167,30 +180,41 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
             w[q] = cvt_f64(isn ? 0.0f : v);
         }
 
-        // ---- B outputs, n-tap chains with static register indices; taps come from the constant bank ----
+        // ---- B outputs: independent n-tap chains with static register indices (taps come from the
+        //      constant bank); kept free of branches so the chains interleave on the float64 pipe ----
+        double res[B];
+#pragma unroll
+        for (int o = 0; o < B; ++o) {
+            double top = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) top = fma(p.taps[k], w[o + 2 * H - k], top);   // out[c] += K[k] v[c + H - k]
+            res[o] = top;
+        }
+        if (nanbits != 0) {
+            // some inputs were NaN: redo the denominator of the outputs whose window saw one
+#pragma unroll
+            for (int o = 0; o < B; ++o) {
+                const uint64_t wb = (nanbits >> o) & ((1ull << NT) - 1ull);
+                if (wb != 0) {
+                    const double bot = smooth_bot_with_nans<H>(sm.taps, wb, p.ksum, p.ntaps);
+                    res[o] = (bot == 0.0) ? (double)centre_filled[o] : res[o] / bot;
+                }
+            }
+        }
 #pragma unroll
         for (int o = 0; o < B; ++o) {
             const int64_t c = c0 + o;
             if (interior || c < p.nchan) {                           // uniform
-                double top = 0.0;
-#pragma unroll
-                for (int k = 0; k < NT; ++k) top = fma(p.taps[k], w[o + 2 * H - k], top);   // out[c] += K[k] v[c + H - k]
-                double res = top;
-                const uint64_t wb = (nanbits >> o) & ((1ull << NT) - 1ull);
-                if (wb != 0) {
-                    const double bot = smooth_bot_with_nans<H>(sm.taps, wb, p.ksum, p.ntaps);
-                    res = (bot == 0.0) ? (double)centre_filled[o] : top / bot;
-                }
                 if (EPI == 0) {
-                    if (active) *reinterpret_cast<float *>(outp) = (float)res;
+                    if (active) *reinterpret_cast<float *>(outp) = (float)res[o];
                     outp += out_step;
                 } else if (EPI == 1) {
-                    if (active) *reinterpret_cast<double *>(outp) = res;
+                    if (active) *reinterpret_cast<double *>(outp) = res[o];
                     outp += out_step;
                 } else {
                     // fused moments: the smoothed value enters as the materialised dtype would hold it,
                     // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
-                    const double sv = p.round_f32 ? (double)(float)res : res;
+                    const double sv = p.round_f32 ? (double)(float)res[o] : res[o];
                     const bool inc = ((incbits >> (o + H)) & 1ull) && sv == sv;
                     if (inc) {
                         const double2 t = __ldg(p.tab + c);

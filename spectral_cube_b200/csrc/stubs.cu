@@ -10,13 +10,4 @@ extern "C" {
 int sc_moments_spatial(const float *, int64_t, int64_t, int64_t, int64_t, int64_t, int,
                        const sc_mask_desc *, const double *, double, int, double *, double *, double *, void *) { SC_STUB("sc_moments_spatial") }
 
-int sc_spectral_interp(const float *, void *, int, uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                       const sc_mask_desc *, double, const double *, const double *, int, double, int, int, int,
-                       void *, size_t, void *) { SC_STUB("sc_spectral_interp") }
-
-int sc_reproject(const float *, void *, int, uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                 const sc_mask_desc *, double, const double *, const double *, int, void *) { SC_STUB("sc_reproject") }
-
-int sc_wcs_pixel_map(const double *, const double *, int64_t, int64_t, double *, double *, void *) { SC_STUB("sc_wcs_pixel_map") }
-
 }

@@ -397,6 +397,127 @@ class BaseSpectralCube(object):
             return self._new_cube_with(data=self._run_spatial_smooth(k2d, _lib.F32))
         return self._new_cube_from_f64(self._run_spatial_smooth(k2d, _lib.F64))
 
+    # -- spectral resampling (spectral_cube.py:3224-3332; dask_spectral_cube.py:1250-1373) --------------
+    def spectral_interpolate(self, spectral_grid, suppress_smooth_warning=False, fill_value=None,
+                             update_function=None, force_rechunk=True, **kwargs):
+        """Resample the cube spectrally onto ``spectral_grid`` (values in the cube's spectral unit,
+        or a Quantity-like with ``.value``); linear interpolation per spaxel."""
+        torch = _torch()
+        lib = _lib.load()
+        grid = np.asarray(getattr(spectral_grid, 'value', spectral_grid), dtype=np.float64)
+        inaxis = self.spectral_axis
+        indiff = np.mean(np.diff(inaxis))
+        outdiff = np.mean(np.diff(grid))
+        reverse_out = outdiff < 0
+        reverse_in = indiff < 0
+        if reverse_out:
+            grid = grid[::-1]
+            outdiff = np.mean(np.diff(grid))
+        if reverse_in:
+            inaxis = inaxis[::-1]
+            indiff = np.mean(np.diff(inaxis))
+        if indiff < 0 or outdiff < 0:
+            raise ValueError("impossible.")
+        assert np.all(np.diff(grid) > 0)
+        assert np.all(np.diff(inaxis) > 0)
+        np.testing.assert_allclose(np.diff(grid), outdiff, err_msg="Output grid must be linear")
+        if outdiff > 2 * indiff and not suppress_smooth_warning:
+            warnings.warn("Input grid has too small a spacing. The data should "
+                          "be smoothed prior to resampling.", SmoothingWarning)
+
+        src = self._data
+        nchan, ny, nx = self.shape
+        nout = grid.size
+        dask = self._mirrors_dask
+        out = torch.empty((nout, ny, nx), dtype=torch.float64 if dask else torch.float32, device=src.device)
+        omask = torch.empty((nout, ny, nx), dtype=torch.uint8, device=src.device)
+        desc, keep = self._mask_desc()
+        ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPECTRAL_INTERP, nchan, ny, nx, nout))
+        (ia, ip), (ga, gp) = _lib.as_double_array(inaxis), _lib.as_double_array(grid)
+        _lib.check(lib.sc_spectral_interp(
+            src.data_ptr(), out.data_ptr(), _lib.F64 if dask else _lib.F32, omask.data_ptr(),
+            nchan, ny, nx, src.stride(0), src.stride(1), nout, desc,
+            float('nan') if dask else float(self._fill_value),           # dask:1308 fills with NaN
+            ip, gp, 0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
+            1 if reverse_in else 0, 1 if reverse_out else 0, 1 if dask else 0,
+            ws.data_ptr(), ws.numel(), _stream()))
+        # new spectral WCS: crpix=1, crval = first grid value as given, cdelt = +-mean spacing (:3317-3324)
+        newwcs = self._wcs.copy()
+        inv = 1.0 / self._spectral_scale
+        newwcs.crpix[2] = 1.0
+        newwcs.crval[2] = (grid[-1] if reverse_out else grid[0]) * inv
+        newwcs.cdelt[2] = (-outdiff if reverse_out else outdiff) * inv
+        newwcs.pc[2, :] = [0.0, 0.0, 1.0]
+        newmask = BooleanArrayMask(omask, wcs=newwcs)
+        if dask:
+            cube = self._new_cube_with(data=out.to(torch.float32), wcs=newwcs, mask=newmask)
+            cube._data_hi = out
+        else:
+            cube = self._new_cube_with(data=out, wcs=newwcs, mask=newmask)
+        cube._mask = newmask
+        return cube
+
+    # -- reprojection (spectral_cube.py:2649-2746) -------------------------------------------------------
+    _ORDERS = {'nearest-neighbor': 0, 'bilinear': 1, 0: 0, 1: 1}
+
+    def _pixel_map(self, wcs_out, ny_out, nx_out):
+        """float64 device planes (yin, xin): where every output pixel falls in this cube's image."""
+        torch = _torch()
+        lib = _lib.load()
+        dev = self._data.device
+        yin = torch.empty((ny_out, nx_out), dtype=torch.float64, device=dev)
+        xin = torch.empty((ny_out, nx_out), dtype=torch.float64, device=dev)
+        (oa, op), (ia, ip) = _lib.as_double_array(wcs_out.celestial_params()), _lib.as_double_array(self._wcs.celestial_params())
+        _lib.check(lib.sc_wcs_pixel_map(op, ip, ny_out, nx_out, yin.data_ptr(), xin.data_ptr(), _stream()))
+        return yin, xin
+
+    def _run_reproject(self, yin, xin, order, filled=True, out_dtype=None):
+        torch = _torch()
+        lib = _lib.load()
+        src = self._data
+        nchan, ny, nx = self.shape
+        ny_out, nx_out = yin.shape
+        out_dtype = _lib.F64 if out_dtype is None else out_dtype
+        out = torch.empty((nchan, ny_out, nx_out), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
+                          device=src.device)
+        foot = torch.empty((nchan, ny_out, nx_out), dtype=torch.uint8, device=src.device)
+        desc, keep = self._mask_desc() if filled else lower_mask(None, src)
+        _lib.check(lib.sc_reproject(src.data_ptr(), out.data_ptr(), out_dtype, foot.data_ptr(), nchan, ny, nx,
+                                    src.stride(0), src.stride(1), ny_out, nx_out, desc, float(self._fill_value),
+                                    yin.data_ptr(), xin.data_ptr(), order, _stream()))
+        return out, foot
+
+    def reproject(self, header, order='bilinear', use_memmap=False, filled=True, **kwargs):
+        """Spatially reproject the cube into a new header (a FITS-header-like mapping with NAXISn and
+        celestial WCS keywords, or a ``CubeWCS`` plus ``shape_out=``)."""
+        torch = _torch()
+        if order not in self._ORDERS:
+            raise NotImplementedError("order=%r: only 'nearest-neighbor' and 'bilinear' are implemented" % (order,))
+        if hasattr(header, 'celestial_params'):
+            newwcs = header
+            shape_out = tuple(kwargs.pop('shape_out'))
+        else:
+            newwcs = as_cube_wcs(header)
+            shape_out = tuple(int(header['NAXIS%d' % (i + 1)]) for i in range(int(header['NAXIS'])))[::-1]
+        if shape_out[0] != self.shape[0]:
+            raise ValueError("reproject() resamples the celestial axes only; use spectral_interpolate for the "
+                             "spectral axis (spectral_cube.py:2656-2657)")
+        if self.size >= MEMORY_THRESHOLD and not self.allow_huge_operations and not kwargs.pop('_allow_huge', True):
+            raise ValueError("This function requires loading the whole cube into memory")      # utils.py:53-67
+        yin, xin = self._pixel_map(newwcs, shape_out[1], shape_out[2])
+        out, foot = self._run_reproject(yin, xin, self._ORDERS[order], filled=filled)
+        if bool(torch.isnan(out).all()):
+            raise ValueError("All values in reprojected cube are nan.  This can be caused"
+                             " by an error in which coordinates do not 'round-trip'.  Try "
+                             "setting ``roundtrip_coords=False``.  You might also check "
+                             "whether the WCS transformation produces valid pixel->world "
+                             "and world->pixel coordinates in each axis.")
+        newmask = BooleanArrayMask(foot, wcs=newwcs)
+        cube = self._new_cube_with(data=out.to(torch.float32), wcs=newwcs, mask=newmask)
+        cube._data_hi = out                        # reproject_interp returns float64
+        cube._mask = newmask
+        return cube
+
     # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
     def _moments_axis0_raw(self, want_bits):
         """Run the fused kernel; returns dict order -> float64 device tensor (ny, nx), with units
