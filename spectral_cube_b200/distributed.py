@@ -1,0 +1,268 @@
+"""
+Spatial-plane sharding across GPUs: one process per GPU, every rank owns a
+contiguous block of image rows ``[:, y0:y1, :]`` with whole spectra and whole rows, so moments,
+spectral smoothing and spectral interpolation need no communication at all.  The only exchanges
+on the path are
+
+  * the ``ceil(k/2)`` halo rows ``spatial_smooth`` needs from the two neighbouring ranks
+    (``exchange_halo_rows``: neighbour send/recv in one batch, or an all-gather of the edge strips
+    as the north star words it), and
+  * one all-to-all re-shard from rows to channels before ``reproject`` (a rotated output row
+    block maps to a slanted strip of the input, so each rank would need remote rows; after the
+    re-shard every rank reprojects whole planes locally).
+
+``torch.distributed`` (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests) is the
+plumbing; tensors are only memory holders.  The reference has no counterpart: its parallelism is
+joblib/dask on one host (spectral_cube.py:2951-3019, dask_spectral_cube.py:501-638).
+"""
+import numpy as np
+
+
+def row_partition(ny, world_size):
+    """Balanced contiguous row blocks: list of (y0, y1) per rank; the first ``ny % world`` ranks get
+    one extra row."""
+    base, extra = divmod(int(ny), int(world_size))
+    out, y = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((y, y + n))
+        y += n
+    return out
+
+
+def channel_partition(nchan, world_size):
+    return row_partition(nchan, world_size)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def exchange_halo_rows(top_edge, bot_edge, group=None, mode='p2p'):
+    """Swap edge strips with the neighbouring ranks.
+
+    ``top_edge`` / ``bot_edge`` are this rank's first / last ``h`` FILLED rows, shape
+    (nchan, h, nx).  Returns ``(halo_top, halo_bot)``: the rows just above this shard (the previous
+    rank's bottom strip) and just below it (the next rank's top strip); ``None`` at the image
+    boundary.  ``mode='p2p'`` moves 2 strips per rank; ``mode='allgather'`` gathers every rank's two
+    strips everywhere (world x the bytes, same result).
+    """
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return None, None
+    halo_top = torch.empty_like(bot_edge) if rank > 0 else None
+    halo_bot = torch.empty_like(top_edge) if rank < world - 1 else None
+    if mode == 'allgather':
+        both = torch.stack([top_edge, bot_edge]).contiguous()
+        gathered = [torch.empty_like(both) for _ in range(world)]
+        dist.all_gather(gathered, both, group=group)
+        if rank > 0:
+            halo_top.copy_(gathered[rank - 1][1])
+        if rank < world - 1:
+            halo_bot.copy_(gathered[rank + 1][0])
+        return halo_top, halo_bot
+    if mode != 'p2p':
+        raise ValueError("mode must be 'p2p' or 'allgather'")
+    ops = []
+    peer = lambda r: dist.get_global_rank(group, r) if group is not None else r
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, top_edge.contiguous(), peer(rank - 1), group))
+        ops.append(dist.P2POp(dist.irecv, halo_top, peer(rank - 1), group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, bot_edge.contiguous(), peer(rank + 1), group))
+        ops.append(dist.P2POp(dist.irecv, halo_bot, peer(rank + 1), group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return halo_top, halo_bot
+
+
+def reshard_rows_to_channels(local, ny_total, group=None):
+    """(nchan, rows_r, nx) row shard -> (chans_r, ny_total, nx) channel shard with one all-to-all."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nchan, _, nx = local.shape
+    cparts = channel_partition(nchan, world)
+    rparts = row_partition(ny_total, world)
+    if world == 1:
+        return local
+    send = [local[c0:c1].contiguous() for (c0, c1) in cparts]
+    my_c0, my_c1 = cparts[rank]
+    recv = [torch.empty((my_c1 - my_c0, y1 - y0, nx), dtype=local.dtype, device=local.device) for (y0, y1) in rparts]
+    dist.all_to_all(recv, send, group=group) if dist.get_backend(group) == 'nccl' else _all_to_all_fallback(recv, send, group)
+    return torch.cat(recv, dim=1)
+
+
+def reshard_channels_to_rows(local, nchan_total, group=None):
+    """(chans_r, ny, nx) channel shard -> (nchan_total, rows_r, nx) row shard."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    _, ny, nx = local.shape
+    cparts = channel_partition(nchan_total, world)
+    rparts = row_partition(ny, world)
+    if world == 1:
+        return local
+    send = [local[:, y0:y1].contiguous() for (y0, y1) in rparts]
+    my_y0, my_y1 = rparts[rank]
+    recv = [torch.empty((c1 - c0, my_y1 - my_y0, nx), dtype=local.dtype, device=local.device) for (c0, c1) in cparts]
+    dist.all_to_all(recv, send, group=group) if dist.get_backend(group) == 'nccl' else _all_to_all_fallback(recv, send, group)
+    return torch.cat(recv, dim=0)
+
+
+def _all_to_all_fallback(recv, send, group):
+    """gloo has no all_to_all: pairwise isend/irecv (CPU tests only)."""
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            recv[r].copy_(send[r])
+            continue
+        reqs.append(dist.isend(send[r], r, group=group))
+        reqs.append(dist.irecv(recv[r], r, group=group))
+    for q in reqs:
+        q.wait()
+
+
+def gather_rows(local_map, ny_total, group=None, dst=None):
+    """Assemble row-sharded 2-D maps (rows_r, nx) into the full (ny_total, nx) map (all ranks, or only
+    ``dst``)."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return local_map
+    parts = row_partition(ny_total, world)
+    nx = local_map.shape[-1]
+    pad = max(y1 - y0 for y0, y1 in parts)
+    buf = torch.zeros((pad, nx), dtype=local_map.dtype, device=local_map.device)
+    buf[:local_map.shape[0]] = local_map
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    if dst is not None and rank != dst:
+        return None
+    return torch.cat([g[:(y1 - y0)] for g, (y0, y1) in zip(gathered, parts)], dim=0)
+
+
+class RowShardedCube(object):
+    """This rank's row block of a cube that is sharded over the spatial plane.
+
+    ``local`` is a ``SpectralCube`` / ``DaskSpectralCube`` holding rows [y0, y1) of the full
+    (nchan, ny_total, nx) cube; its WCS is the FULL cube's WCS with CRPIX2 shifted by -y0, so world
+    coordinates of local pixels are the global ones.
+    """
+
+    def __init__(self, local, ny_total, y0, group=None):
+        self.local, self.ny_total, self.y0, self.group = local, int(ny_total), int(y0), group
+
+    @classmethod
+    def from_full_wcs(cls, cube_cls, local_data, full_wcs, ny_total, group=None, **kw):
+        dist = _dist()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        y0, y1 = row_partition(ny_total, world)[rank]
+        assert local_data.shape[1] == y1 - y0, "local block has %d rows, expected %d" % (local_data.shape[1], y1 - y0)
+        w = full_wcs.copy()
+        w.crpix[1] -= y0
+        return cls(cube_cls(local_data, w, **kw), ny_total, y0, group)
+
+    @property
+    def shape(self):
+        return (self.local.shape[0], self.ny_total, self.local.shape[2])
+
+    def _wrap(self, local):
+        return RowShardedCube(local, self.ny_total, self.y0, self.group)
+
+    def with_mask(self, mask, **kw):
+        return self._wrap(self.local.with_mask(mask, **kw))
+
+    def __gt__(self, v):
+        return self.local > v
+
+    def __lt__(self, v):
+        return self.local < v
+
+    # ---- embarrassingly parallel over spaxels: no communication ------------------------------------
+    def moment(self, order=0, axis=0, gather=False, **kw):
+        if axis != 0:
+            raise NotImplementedError("row-sharded moments are along the spectral axis")
+        m = self.local.moment(order=order, axis=0, **kw)
+        return m if not gather else self.gather_map(m)
+
+    def moment0(self, **kw):
+        return self.moment(order=0, **kw)
+
+    def moment1(self, **kw):
+        return self.moment(order=1, **kw)
+
+    def moment2(self, **kw):
+        return self.moment(order=2, **kw)
+
+    def gather_map(self, proj):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(proj.value))
+        dev = self.local._data.device
+        full = gather_rows(t.to(dev), self.ny_total, self.group)
+        return full.cpu().numpy()
+
+    def spectral_smooth(self, kernel, **kw):
+        return self._wrap(self.local.spectral_smooth(kernel, **kw))
+
+    def spectral_interpolate(self, grid, **kw):
+        return self._wrap(self.local.spectral_interpolate(grid, **kw))
+
+    # ---- spatial_smooth: halo rows from the two neighbours ---------------------------------------------
+    def spatial_smooth(self, kernel, halo_mode='p2p', **kw):
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        loc = self.local
+        loc.check_jybeam_smoothing(raise_error_jybm=kw.pop('raise_error_jybm', True))
+        k2d = loc._kernel_array(kernel, 2)
+        h = k2d.shape[0] // 2
+        nchan, ny, nx = loc.shape
+        if h > ny:
+            raise ValueError("kernel half-height %d exceeds the %d rows of this shard" % (h, ny))
+        src = loc._data
+        desc, keep = loc._mask_desc()
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def pack(row0):
+            out = torch.empty((nchan, h, nx), dtype=torch.float32, device=src.device)
+            _lib.check(lib.sc_pack_filled_rows(src.data_ptr(), nchan, ny, nx, src.stride(0), src.stride(1), desc,
+                                               float(loc._fill_value), row0, h, out.data_ptr(), stream))
+            return out
+        halo_top = halo_bot = None
+        if h > 0:
+            halo_top, halo_bot = exchange_halo_rows(pack(0), pack(ny - h), self.group, mode=halo_mode)
+        dask = loc._mirrors_dask
+        out = loc._run_spatial_smooth(k2d, _lib.F32 if dask else _lib.F64, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h)
+        new = loc._new_cube_with(data=out) if dask else loc._new_cube_from_f64(out)
+        return self._wrap(new)
+
+    # ---- reproject: one re-shard to channels, then whole planes locally -------------------------------
+    def reproject(self, header, order='bilinear', filled=True, **kw):
+        """Returns a ``ChannelShardedCube``-like pair: (local cube of this rank's channels over the
+        full output plane, (c0, c1)).  Masked voxels are filled BEFORE the re-shard so lazy masks
+        (which refer to the row-sharded data) never have to travel."""
+        dist = _dist()
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        loc = self.local
+        filled_rows = loc._filled_tensor(loc._fill_value) if filled else loc._data
+        chan_local = reshard_rows_to_channels(filled_rows, self.ny_total, self.group)
+        c0, c1 = channel_partition(loc.shape[0], world)[rank]
+        w = loc._wcs.copy()
+        w.crpix[1] += self.y0                                  # back to the full image's WCS
+        w.crpix[2] -= c0
+        sub = type(loc)(chan_local, w, unit=loc._unit, fill_value=loc._fill_value, spectral_unit=loc._spectral_unit)
+        if hasattr(header, 'celestial_params'):
+            so = tuple(kw.pop('shape_out'))
+            kw['shape_out'] = (c1 - c0,) + so[1:]
+            return sub.reproject(header, order=order, filled=False, **kw), (c0, c1)
+        hdr = dict(header)
+        hdr['NAXIS3'] = c1 - c0
+        hdr['CRPIX3'] = hdr.get('CRPIX3', 1.0) - c0
+        return sub.reproject(hdr, order=order, filled=False, **kw), (c0, c1)

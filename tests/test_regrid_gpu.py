@@ -177,7 +177,7 @@ def test_reproject_shape_and_wcs():
     assert out.shape == (4, 5, 4)
     assert out.wcs.crpix[0] == hdr['CRPIX1'] and out.wcs.cdelt[0] == hdr['CDELT1']
     # shifted by exactly one pixel: interior values are the input values
-    np.testing.assert_allclose(data_of(out)[:, 1:4, 1:3], G.adv_data(), rtol=1e-9)
+    np.testing.assert_allclose(data_of(out)[:, 1:4, 1:3], G.adv_data().astype(np.float32), rtol=1e-9)   # the cube holds float32
     assert np.isnan(data_of(out)[:, 0, :]).all()
     assert not out.mask.include()[:, 0, :].any() and out.mask.include()[:, 1:4, 1:3].all()
 
