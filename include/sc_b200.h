@@ -155,6 +155,12 @@ int sc_moments_spatial(const float *cube, int64_t nchan, int64_t ny, int64_t nx,
                        int want_bits, double *out_m0, double *out_m1, double *out_m2,
                        void *stream);
 
+/* Cumulative great-circle pixel offsets from the cube face along numpy axis 1 (y) or 2 (x)
+ * (`_pix_cen()[1]`, `[2]`, spectral_cube.py:1477-1492): float64 (ny, nx) DEVICE plane, in degrees.
+ * wcs = the 12 doubles of sc_wcs_pixel_map; workspace >= ny*nx*16 + 256 bytes. */
+int sc_pixel_offsets(const double *wcs, int64_t ny, int64_t nx, int axis, double *offsets,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* Host-buffer pipeline for the moment maps: `cube_host` is a HOST float32 array (pinned
  * or pageable) with the strides given; row blocks are streamed through two device
  * staging buffers (copy/compute overlap) and the three maps land in HOST float64

@@ -57,6 +57,7 @@ SIGNATURES = {
                                        _vp, _vp, _sz, _vp]),
     'sc_moments_spatial': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _pmask, _vp, _dbl, _i32,
                                   _vp, _vp, _vp, _vp]),
+    'sc_pixel_offsets': (_i32, [_pd, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     'sc_moments_axis0_host': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _pmask, _pd, _dbl, _dbl, _i32,
                                      _vp, _vp, _vp, _sz, _i32]),
     'sc_spectral_smooth': (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,

@@ -595,8 +595,32 @@ class BaseSpectralCube(object):
             xptr, centre.data_ptr(), int(order), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         return out.cpu().numpy()
 
+    def _pixel_offsets(self, axis):
+        """``_pix_cen()[axis]`` for a spatial axis as a (ny, nx) float64 device plane (degrees)."""
+        torch = _torch()
+        lib = _lib.load()
+        nchan, ny, nx = self.shape
+        off = torch.empty((ny, nx), dtype=torch.float64, device=self._data.device)
+        ws = self._get_workspace(ny * nx * 16 + 512)
+        wa, wp = _lib.as_double_array(self._wcs.celestial_params())
+        _lib.check(lib.sc_pixel_offsets(wp, ny, nx, axis, off.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return off
+
     def _moment_spatial(self, order, axis):
-        raise NotImplementedError("moments along spatial axes are not built yet in this round")
+        torch = _torch()
+        lib = _lib.load()
+        if order not in (0, 1, 2):
+            raise NotImplementedError("moments of order > 2 along spatial axes")
+        nchan, ny, nx = self.shape
+        src = self._data
+        off = self._pixel_offsets(axis)
+        out = torch.empty((nchan, nx if axis == 1 else ny), dtype=torch.float64, device=src.device)
+        desc, keep = self._mask_desc()
+        ptrs = [out.data_ptr() if o == order else None for o in (0, 1, 2)]
+        _lib.check(lib.sc_moments_spatial(src.data_ptr(), nchan, ny, nx, src.stride(0), src.stride(1), axis, desc,
+                                          off.data_ptr(), float(self._pix_size_slice(axis)), 1 << order,
+                                          ptrs[0], ptrs[1], ptrs[2], _stream()))
+        return out.cpu().numpy()
 
     def _materialized(self):
         return self

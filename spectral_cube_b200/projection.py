@@ -89,6 +89,6 @@ class Projection(LowerDimensionalObject):
     """2-D result (moment maps).  lower_dimensional_structures.py:246-292."""
 
     def __new__(cls, value, unit=None, wcs=None, meta=None, header=None, copy=True):
-        if np.ndim(value) != 2:
+        if np.ndim(value) != 2:  # noqa
             raise ValueError("value should be a 2-d array")
         return super(Projection, cls).__new__(cls, value, unit=unit, wcs=wcs, meta=meta, header=header, copy=copy)

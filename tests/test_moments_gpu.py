@@ -291,3 +291,53 @@ def test_properties_at_scale():
     np.testing.assert_allclose(b2.value[okm], a2.value[okm], rtol=1e-9, atol=1e-3)
     # (4) M2 >= 0 wherever the mask keeps only positive weights, up to rounding
     assert np.nanmin(a2.value) > -1e-3
+
+
+# ---- moments along the spatial axes (spectral_cube/tests/test_moments.py:22-27, 33-38, 43-48) -------
+@pytest.mark.parametrize('use_dask', [False, True])
+@pytest.mark.parametrize('axis', [1, 2])
+@pytest.mark.parametrize('order', [0, 1, 2])
+def test_reference_spatial_axes(order, axis, use_dask):
+    sc = gpu_cube(G.moment_cube_data(), G.MOMENT_WCS, use_dask=use_dask)
+    mom = quiet(sc.moment, order=order, axis=axis)
+    np.testing.assert_allclose(mom.value, G.MOMENTS[order][axis], rtol=1e-7)
+    assert mom.unit == G.MOMENT_UNITS[order][axis]
+
+
+@pytest.mark.parametrize('axis', [1, 2])
+def test_spatial_axis_moments_match_oracle(axis):
+    data = _random_cube((6, 40, 70), seed=90 + axis, nan_frac=0.03) + np.float32(5.0)
+    w = dict(BENCH_WCS)
+    w['crpix'] = [30.0, 22.0, 1.0]
+    sc, oc = gpu_cube(data, w), oracle_cube(data, w)
+    sc, oc = sc.with_mask(sc > 2.0), oc.with_mask(oc > 2.0)
+    for order in (0, 1, 2):
+        want = quiet(oc.moment, order=order, axis=axis, how='cube')[0]
+        got = quiet(sc.moment, order=order, axis=axis).value
+        assert_maps_close(got, want, rtol=RTOL, atol=1e-16, what='axis %d order %d' % (axis, order))
+
+
+def test_host_pipeline_matches_device_path():
+    """sc_moments_axis0_host (pinned/pageable host cube streamed in row blocks) == resident-cube path."""
+    import ctypes as C
+    import torch
+    from spectral_cube_b200 import _lib
+    from spectral_cube_b200.masks import lower_mask
+    lib = _lib.load()
+    data = _random_cube((40, 37, 96), seed=123)
+    sc = gpu_cube(data, BENCH_WCS)
+    sc = sc.with_mask(sc > 1.0)
+    ref = [m.value for m in sc.moments012()]
+    desc, keep = lower_mask(sc._mask, sc._data)
+    for i in range(desc.n_nodes):                     # the host pipeline sees the cube as "self"
+        desc.nodes[i].data = None
+    host = np.ascontiguousarray(data)
+    outs = [np.empty((37, 96)) for _ in range(3)]
+    xoff, xptr = _lib.as_double_array(sc._spectral_offsets())
+    for staging in (0, 40 * 96 * 4 * 2 * 5):          # default blocks, and 5-row blocks
+        _lib.check(lib.sc_moments_axis0_host(host.ctypes.data, 40, 37, 96, 37 * 96, 96, desc, xptr,
+                                             float(sc._pix_size_slice(0)), sc._world0_spectral(), 7,
+                                             outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data,
+                                             staging, torch.cuda.current_device()))
+        for o in range(3):
+            np.testing.assert_array_equal(outs[o], ref[o])
