@@ -107,6 +107,13 @@ int build_dev_mask(const sc_mask_desc *m, const float *cube, int64_t stride_c, i
         if (nd.kind == SC_MASK_BOOL)
             SC_CHECK_ARG(nd.array && nd.array_dtype == SC_U8, "mask: node %d needs a uint8 array", i);
     }
+    // the node program is always carried (self references normalised to NULL) so a kernel may fall
+    // back to interpreting it even when the interval form exists
+    out->prog = *m;
+    for (int i = 0; i < m->n_nodes; ++i) {
+        sc_mask_node &nd = out->prog.nodes[i];
+        if (nd.kind <= SC_MASK_CMP_ARRAY && node_is_self(nd, cube, stride_c, stride_y)) nd.data = nullptr;
+    }
     float lo = -INFINITY, hi = INFINITY;
     int root = m->n_nodes - 1;
     // The interval form excludes +-inf at open ends, so it is only valid when isfinite is part

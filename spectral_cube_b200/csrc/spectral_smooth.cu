@@ -5,34 +5,49 @@
 // (spectral_cube.py:3186-3222 through :3103-3159 and :147-158; dask_spectral_cube.py:880-917).
 // astropy semantics: true convolution (kernel flipped), zero-filled boundary whose zeros are
 // VALID samples, out = sum_k K[k] v[c-k] [v not NaN] / sum_k K[k] [v not NaN] in float64,
-// denominator 0 keeps the input NaN.  Masked voxels are replaced by `fill` before convolving.
+// denominator 0 keeps the input value.  Masked voxels are replaced by `fill` before convolving.
 //
-// Kernel (smooth_tma_kernel): a CTA owns SM_TILE adjacent spaxels of one image row (one per
-// consumer thread).  A producer warp streams blocks of B channels x SM_TILE floats through a
-// shared-memory ring with `cp.async.bulk` (TMA) + mbarriers.  For every block of B output
-// channels a consumer thread pulls the B + 2H inputs it needs from three neighbouring ring
-// stages into registers as float64 (mask/fill applied, NaN -> 0 with a bit recorded), then
-// evaluates B independent n-tap FMA chains with compile-time register indices.  The
-// denominator is the kernel sum unless the window's NaN bits are set (rare), in which case the
-// missing taps are subtracted one by one.  Outputs are stored straight from registers
-// (a warp writes 128 contiguous bytes per channel) or, in the fused variant, rounded to the
-// smoothed cube's dtype and accumulated into the moment sums -- the smoothed cube is never
-// written.  The float64 pipe is the co-limiter here: n FMAs per voxel against 8 B of traffic.
+// Kernel (smooth_tma_kernel).  A CTA owns SM_TILE adjacent spaxels of one image row, one per
+// thread.  Warp 0 streams blocks of B channels x SM_TILE floats (one `cp.async.bulk` / TMA row
+// copy of 1 KB per channel) through a STAGES-deep shared-memory ring guarded by full/empty
+// mbarriers, keeping STAGES-2 blocks in flight ahead of the arithmetic.  Per block of B output
+// channels a thread
+//   * takes its B NEW inputs from the ring (every sample is loaded from shared memory, masked
+//     and widened to float64 exactly once; the 2H older inputs it still needs stay in registers:
+//     for 2H <= B they are simply the tail of the previous block's array -- the loop is unrolled
+//     by two and the two arrays swap roles, so no register is moved),
+//   * widens float32 -> float64 WITHOUT the conversion unit: the float's bits are placed in the
+//     double's fields (one 64-bit multiply-shift + one AND), which yields v * 2^-896 exactly for
+//     every finite v including zeros and denormals; the taps are pre-scaled by 2^896 on the host
+//     so every product and sum is bit-identical to the unscaled arithmetic.  (F2F runs at ~9
+//     lanes/clk/SM on this part and was the top limiter of the first version.)
+//   * runs B independent n-tap FMA chains with compile-time register indices and taps read
+//     from the constant bank, branch-free so the chains interleave on the float64 pipe,
+//   * fixes up the denominator only where the rolling NaN bit mask says a window saw a NaN:
+//     sum of the PRESENT taps from a 6-bit-chunk look-up table in shared memory.
+// Outputs are stored straight from registers (a warp writes 128 contiguous bytes per channel) or,
+// in the fused variant, rounded to the smoothed cube's dtype and accumulated into the moment sums
+// under the include mask of the ORIGINAL data -- the smoothed cube is never written.
 #include "common.cuh"
 #include "tma.cuh"
+#include <type_traits>
 
 namespace scb {
 
 int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
 int env_int(const char *name, int dflt);
 
-constexpr int SM_TILE = 128;                 // spaxels per CTA = consumer threads
-constexpr int SM_THREADS = SM_TILE + 32;
+constexpr int SM_TILE = 256;                 // spaxels per CTA = threads (1 KB row bursts)
+constexpr int SM_THREADS = SM_TILE;          // warp 0 also issues the TMA copies
+constexpr int SM_MIN_CTAS = 2;               // register budget: 128 per thread
 constexpr int SM_MAX_TAPS = 2 * 16 + 1;
+constexpr int SM_LUT_CHUNKS = (SM_MAX_TAPS + 5) / 6;
+constexpr int SM_B = 16;                     // output channels per block
+constexpr int SM_STAGES = 6;
 
 struct SmoothParams {
     const float *in;
-    void *out;                               // float32 or float64 (OUT64)
+    void *out;                               // float32 or float64
     int64_t nchan, ny, nx;
     int64_t stride_c, stride_y, out_stride_c, out_stride_y;
     int tiles_per_row;
@@ -40,6 +55,8 @@ struct SmoothParams {
     float fill;
     double ksum;                             // sum of the normalised taps (~1)
     double taps[SM_MAX_TAPS];                // normalised, centred in a 2H+1 window, zero padded
+    double taps_scaled[SM_MAX_TAPS];         // the same times 2^896 (see place_scaled)
+    int debug;                               // experiments only: 1 = skip stores, 2 = skip the tap chains
     int passthrough_spaxels;                 // numpy class: spaxels with nothing included are copied through
     // fused moments
     const double2 *tab;                      // {d, d^2} per channel
@@ -49,63 +66,183 @@ struct SmoothParams {
     DevMask mask;
 };
 
-template <int B, int STAGES>
 struct SmoothSmem {
-    float data[STAGES][B][SM_TILE];
+    float data[SM_STAGES][SM_B][SM_TILE];
     double taps[SM_MAX_TAPS];
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+    double lut[SM_LUT_CHUNKS][64];           // lut[ch][m] = sum of taps whose window bits (6 ch + b) are set in m
+    double rlut1[SM_MAX_TAPS];               // rlut1[j] = 1 / (sum of all taps but the one under window bit j)
+    uint64_t full[SM_STAGES];
+    uint64_t empty[SM_STAGES];
 };
 
-// float32 -> float64 through an opaque conversion so the NaN select stays on the float32 side
-__device__ __forceinline__ double cvt_f64(float v) {
-    double d;
-    asm("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(v));
-    return d;
+// v * 2^-896 as a double, exactly, for every finite v (zeros and denormals included): the float's
+// exponent and mantissa fields are dropped into the double's.  hi:lo = (int64)bits << 29, then the
+// three sign-extension bits below the sign are cleared.  +-inf keeps being +-inf when KEEP_INF.
+template <bool KEEP_INF>
+__device__ __forceinline__ double place_scaled(float v) {
+    const int b = __float_as_int(v);
+    const long long t = (long long)b << 29;
+    int hi = (int)(t >> 32) & 0x8FFFFFFF;
+    if (KEEP_INF && (b & 0x7F800000) == 0x7F800000) hi |= 0x7FF00000;
+    return __hiloint2double(hi, (int)t);
 }
 
-// Rare path: some inputs of this output's window are NaN.  `wb` has bit j set when window entry j
-// (input o + j, tap 2H - j) is NaN.  Subtract the missing taps from the full kernel sum; if every
-// real tap is missing the denominator is exactly 0.
+// Denominator of a window with missing (NaN) inputs: `present` has bit j set when window entry j
+// (input o + j, tap 2H - j) is a number.  Sum of the present taps, six window bits per table look-up;
+// exactly 0 when nothing is present.
 template <int H>
-__device__ __noinline__ double smooth_bot_with_nans(const double *taps_sm, uint64_t wb, double ksum, int ntaps) {
-    constexpr uint64_t FULL = (1ull << (2 * H + 1)) - 1ull;
-    if (wb == FULL) return 0.0;                              // whole window missing (blank spectra)
-    const int h = ntaps >> 1;
-    if (__popcll(wb) > H) {
-        // mostly missing: add up what is there (taps outside the real kernel are zero)
-        double bot = 0.0;
-        uint64_t good = ~wb & FULL;
-        while (good) {
-            const int j = __ffsll((long long)good) - 1;
-            good &= good - 1;
-            bot += taps_sm[2 * H - j];
+__device__ __forceinline__ double smooth_bot_present(const double (*lut)[64], uint64_t present) {
+    constexpr int NCH = (2 * H + 1 + 5) / 6;
+    double bot = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) bot += lut[ch][(present >> (6 * ch)) & 63u];
+    return bot;
+}
+
+// In the smoothing kernels MODE_INTERVAL means "interval mask AND the fill value is NaN" (the host
+// sends finite fills to MODE_GENERIC), so "excluded" and "NaN" collapse into one test.
+template <int MODE, int EPI, typename bits_t>
+__device__ __forceinline__ double smooth_take(const SmoothParams &p, float v, bool valid, int q, int64_t cc, int64_t y, int64_t x,
+                                              bits_t &nanbits, bits_t &incbits, bool &any_included) {
+    // `valid` (uniform): the channel exists; beyond the cube the sample is a VALID zero that no mask touches
+    if (MODE == MODE_INTERVAL) {
+        const bool inr = (v > p.mask.lo) & (v < p.mask.hi);
+        const bool use = inr & valid;                    // a real, included, finite sample
+        if (EPI == 2) incbits |= (bits_t)(use ? 1u : 0u) << q;
+        else any_included |= use;
+        nanbits |= (bits_t)((inr | !valid) ? 0u : 1u) << q;
+        return place_scaled<false>(use ? v : 0.0f);
+    }
+    const bool inc = valid && mask_include<MODE>(p.mask, v, cc, y, x);
+    if (EPI == 2) incbits |= (bits_t)((inc && v == v) ? 1u : 0u) << q;
+    else if (MODE != MODE_NONE) any_included |= inc;
+    v = valid ? (inc ? v : p.fill) : 0.0f;
+    const bool isn = v != v;
+    nanbits |= (bits_t)(isn ? 1u : 0u) << q;
+    return place_scaled<true>(isn ? 0.0f : v);
+}
+
+struct SmoothAcc { double s0, s1, s2; int cnt; };
+
+// Rare path, one copy in the binary: the window of this output saw missing (NaN) inputs; `wb` has
+// bit j set when window entry j is missing.  Returns top / bot, or the (filled) input value when
+// nothing under the kernel is valid.
+template <int H, int MODE, typename bits_t>
+__device__ __noinline__ double smooth_fix(const SmoothParams &p, const SmoothSmem &sm, double top, bits_t wb,
+                                          const float *centre, bool centre_valid, int64_t c, int64_t y, int64_t x) {
+    constexpr bits_t FULL = (bits_t)((1ull << (2 * H + 1)) - 1ull);
+    const double bot = wb == FULL ? 0.0 : smooth_bot_present<H>(sm.lut, (uint64_t)(bits_t)(~wb & FULL));
+    if (bot != 0.0) return top / bot;
+    float cv = 0.0f;                                             // nothing valid under the kernel
+    if (centre_valid) {
+        cv = *centre;
+        if (!mask_include<MODE>(p.mask, cv, c, y, x)) cv = p.fill;
+    }
+    return (double)cv;
+}
+
+// One block of B outputs.  `car` = the 2H inputs before this block's new ones (window entries
+// [0, 2H)), `cur` receives the B new inputs (entries [2H, 2H+B)).
+template <int H, int MODE, int EPI, typename bits_t, int NCAR>
+__device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &sm, const double (&car)[NCAR], int car_off,
+                                             double (&cur)[SM_B], const float *pcur, const float *pnext,
+                                             int64_t c0, int64_t y, int64_t x, bool active,
+                                             bits_t &nanbits, bits_t &incbits, bool &any_included,
+                                             char *&outp, int64_t out_step, SmoothAcc &acc) {
+    constexpr int B = SM_B, NT = 2 * H + 1;
+    // ---- the B new inputs: channels [c0+H, c0+B+H) = rows [H, B) of this stage, rows [0, H) of the next ----
+#pragma unroll
+    for (int n = 0; n < B; ++n) {
+        const int q = 2 * H + n;
+        const int64_t cc = c0 + H + n;                           // uniform across the CTA
+        // the ring row is always addressable; beyond the cube it holds stale bytes that `valid` discards
+        const float v = (n < B - H) ? pcur[(n + H) * SM_TILE] : pnext[(n + H - B) * SM_TILE];
+        cur[n] = smooth_take<MODE, EPI, bits_t>(p, v, cc < p.nchan, q, cc, y, x, nanbits, incbits, any_included);
+    }
+    // ---- blank spectra (every sample of every lane's window missing, e.g. the blanked frame of a mosaic):
+    //      the result is the filled input itself, no arithmetic needed ----
+    constexpr bits_t ALLBITS = (bits_t)(~(bits_t)0) >> (8 * sizeof(bits_t) - (B + 2 * H));
+    if (EPI != 2 && __all_sync(0xffffffffu, nanbits == ALLBITS)) {
+#pragma unroll
+        for (int o = 0; o < B; ++o) {
+            if (c0 + o < p.nchan && active) {
+                float cv = pcur[o * SM_TILE];
+                if (!mask_include<MODE>(p.mask, cv, c0 + o, y, x)) cv = p.fill;
+                if (EPI == 0) *reinterpret_cast<float *>(outp + o * out_step) = cv;
+                else          *reinterpret_cast<double *>(outp + o * out_step) = (double)cv;
+            }
         }
-        return bot;
+        outp += B * out_step;
+        nanbits >>= B;
+        incbits >>= B;
+        return;
     }
-    double bot = ksum;
-    int nbad = 0;
-    while (wb) {
-        const int j = __ffsll((long long)wb) - 1;
-        wb &= wb - 1;
-        const int k = 2 * H - j;
-        bot -= taps_sm[k];
-        nbad += (k >= H - h && k <= H + h) ? 1 : 0;
+    // ---- B independent n-tap chains; window entry q is car[car_off + q] for q < 2H, cur[q - 2H] after ----
+    double res[B];
+#pragma unroll
+    for (int o = 0; o < B; ++o) {
+        double top = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const int q = o + 2 * H - k;                         // out[c] += K[k] v[c + H - k]
+            top = fma(p.taps_scaled[k], q < 2 * H ? car[car_off + q] : cur[q - 2 * H], top);
+        }
+        res[o] = top;
     }
-    return nbad >= ntaps ? 0.0 : bot;
+    if (nanbits != 0) {
+        // some inputs were NaN: redo the denominator of the outputs whose window saw one
+        constexpr bits_t FULL = (bits_t)((1ull << NT) - 1ull);
+#pragma unroll
+        for (int o = 0; o < B; ++o) {
+            const bits_t wb = (bits_t)(nanbits >> o) & FULL;
+            if (wb != 0) {
+                const int j = (8 * (int)sizeof(bits_t) - 1) - (sizeof(bits_t) == 4 ? __clz((int)wb) : __clzll((long long)wb));
+                const double r1 = sm.rlut1[j];
+                if ((wb & (wb - 1)) == 0 && r1 != 0.0) res[o] *= r1;      // one input missing: tabulated 1/bot
+                else res[o] = smooth_fix<H, MODE, bits_t>(p, sm, res[o], wb, pcur + o * SM_TILE, c0 + o < p.nchan, c0 + o, y, x);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < B; ++o) {
+        const int64_t c = c0 + o;
+        if (c < p.nchan) {                                       // uniform
+            if (EPI == 0) {
+                if (active) *reinterpret_cast<float *>(outp + o * out_step) = (float)res[o];
+            } else if (EPI == 1) {
+                if (active) *reinterpret_cast<double *>(outp + o * out_step) = res[o];
+            } else {
+                // fused moments: the smoothed value enters as the materialised dtype would hold it,
+                // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
+                const double sv = p.round_f32 ? (double)(float)res[o] : res[o];
+                const bool inc = ((incbits >> (o + H)) & 1u) && sv == sv;
+                if (inc) {
+                    const double2 t = __ldg(p.tab + c);
+                    acc.s0 += sv;
+                    acc.s1 = fma(sv, t.x, acc.s1);
+                    acc.s2 = fma(sv, t.y, acc.s2);
+                    acc.cnt += 1;
+                }
+            }
+        }
+    }
+    outp += B * out_step;
+    nanbits >>= B;
+    incbits >>= B;
 }
 
 // EPI 0: store float32, 1: store float64, 2: fused moments
-template <int H, int B, int STAGES, int MODE, int EPI>
-__global__ void __launch_bounds__(SM_THREADS)
+template <int H, int MODE, int EPI>
+__global__ void __launch_bounds__(SM_THREADS, SM_MIN_CTAS)
 smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
+    constexpr int B = SM_B, STAGES = SM_STAGES;
     constexpr int NT = 2 * H + 1;
     constexpr int NIN = B + 2 * H;
-    static_assert(H <= B, "window must fit in neighbouring stages");
+    using bits_t = typename std::conditional<(NIN <= 32), uint32_t, uint64_t>::type;
+    static_assert(H <= B, "window must fit in two neighbouring stages");
     static_assert(NIN <= 64, "NaN bit mask is 64 bits");
-    static_assert(STAGES >= 4, "three stages are read while one is being filled");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SmoothSmem<B, STAGES> &sm = *reinterpret_cast<SmoothSmem<B, STAGES> *>(smem_raw);
+    SmoothSmem &sm = *reinterpret_cast<SmoothSmem *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -121,115 +258,80 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     }
     if (tid < NT) sm.taps[tid] = p.taps[tid];
     __syncthreads();
-
-    if (warp == SM_TILE / 32) {
-        // ---------------- producer warp ----------------
-        const float *src = p.in + y * p.stride_y + x0;
-        const uint64_t pol = l2_evict_first_policy();
-        const uint32_t row_bytes = (uint32_t)width * 4u;
-        for (int j = 0; j < nblk; ++j) {
-            const int s = j % STAGES;
-            const int64_t c0 = (int64_t)j * B;
-            const int nch = (int)min((int64_t)B, p.nchan - c0);
-            if (j >= STAGES) mbar_wait(&sm.empty[s], ((j / STAGES) - 1) & 1);
-            if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)nch * row_bytes);
-            __syncwarp();
-            if (lane < nch)
-                tma_load_1d(&sm.data[s][lane][0], src + (c0 + lane) * p.stride_c, row_bytes, &sm.full[s], pol);
+    for (int e = tid; e < ((NT + 5) / 6) * 64; e += SM_THREADS) {
+        const int ch = e >> 6, m = e & 63;
+        double a = 0.0;
+        for (int b = 0; b < 6; ++b) {
+            const int j = 6 * ch + b;                                // window bit j <-> tap 2H - j
+            if (((m >> b) & 1) && j < NT) a += sm.taps[2 * H - j];
         }
-        return;
+        sm.lut[ch][m] = a;
     }
+    if (tid < NT) {
+        double a = 0.0;                                              // same summation order as the LUT path
+        for (int j = 0; j < NT; ++j) if (j != tid) a += sm.taps[2 * H - j];
+        sm.rlut1[tid] = a != 0.0 ? 1.0 / a : 0.0;
+    }
+    __syncthreads();
 
-    // ---------------- consumer warps ----------------
+    // Warp 0 doubles as the producer: block j is loaded into ring slot j % STAGES as soon as every warp
+    // has released the block that used the slot before (STAGES - 2 blocks stay in flight ahead of the math).
+    const float *gsrc = p.in + y * p.stride_y + x0;
+    const uint64_t pol = l2_evict_first_policy();
+    const uint32_t row_bytes = (uint32_t)width * 4u;
+    auto issue_block = [&](int j) {
+        const int s = j % STAGES;
+        const int64_t cj = (int64_t)j * B;
+        const int nch = (int)min((int64_t)B, p.nchan - cj);
+        if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)nch * row_bytes);
+        __syncwarp();
+        if (lane < nch)
+            tma_load_1d(&sm.data[s][lane][0], gsrc + (cj + lane) * p.stride_c, row_bytes, &sm.full[s], pol);
+    };
+    if (warp == 0)
+        for (int j = 0; j < STAGES - 1 && j < nblk; ++j) issue_block(j);
+
     const bool active = tid < width;
     const int64_t x = x0 + tid;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    int cnt = 0;
+    SmoothAcc acc{0.0, 0.0, 0.0, 0};
     bool any_included = false;                                       // for the pass-through fix-up
     char *outp = reinterpret_cast<char *>(p.out) + ((EPI == 1) ? 8 : 4) * (y * p.out_stride_y + x);
     const int64_t out_step = ((EPI == 1) ? 8 : 4) * p.out_stride_c;
+    bits_t nanbits = 0, incbits = 0;
 
-    int sprev = STAGES - 1, scur = 0, snext = 1;                     // ring slots of blocks i-1, i, i+1
+    // window storage: the 2H carried inputs and the B new ones
+    double car[2 * H], cur[B];
+
+    // prologue: channels [-H, 0) are (valid) zeros, channels [0, H) come from the first stage; they
+    // form window entries [0, 2H) of block 0
     mbar_wait(&sm.full[0], 0);
-    for (int i = 0; i < nblk; ++i) {
-        const int64_t c0 = (int64_t)i * B;
-        if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
-        const float *pprev = &sm.data[sprev][B - H][tid];
-        const float *pcur = &sm.data[scur][0][tid];
-        const float *pnext = &sm.data[snext][0][tid];
-        const bool interior = (i >= 1) && (c0 + B + H <= p.nchan);   // every input channel exists
-
-        // ---- gather the B + 2H inputs as float64, apply mask/fill, record NaN and include bits ----
-        double w[NIN];
-        uint64_t nanbits = 0, incbits = 0;
-        float centre_filled[B];
 #pragma unroll
-        for (int q = 0; q < NIN; ++q) {
-            const int64_t cc = c0 - H + q;                           // uniform across the CTA
-            float v = 0.0f;
-            if (interior || (cc >= 0 && cc < p.nchan)) {
-                v = (q < H) ? pprev[q * SM_TILE] : (q < H + B ? pcur[(q - H) * SM_TILE] : pnext[(q - H - B) * SM_TILE]);
-                const bool inc = mask_include<MODE>(p.mask, v, cc, y, x);
-                if (EPI == 2 && inc && v == v) incbits |= 1ull << q;
-                if (EPI != 2 && MODE != MODE_NONE && q >= H && q < H + B) any_included |= inc;
-                v = inc ? v : p.fill;
-            }
-            if (q >= H && q < H + B) centre_filled[q - H] = v;
-            const bool isn = v != v;
-            if (isn) nanbits |= 1ull << q;
-            w[q] = cvt_f64(isn ? 0.0f : v);
-        }
-
-        // ---- B outputs: independent n-tap chains with static register indices (taps come from the
-        //      constant bank); kept free of branches so the chains interleave on the float64 pipe ----
-        double res[B];
-#pragma unroll
-        for (int o = 0; o < B; ++o) {
-            double top = 0.0;
-#pragma unroll
-            for (int k = 0; k < NT; ++k) top = fma(p.taps[k], w[o + 2 * H - k], top);   // out[c] += K[k] v[c + H - k]
-            res[o] = top;
-        }
-        if (nanbits != 0) {
-            // some inputs were NaN: redo the denominator of the outputs whose window saw one
-#pragma unroll
-            for (int o = 0; o < B; ++o) {
-                const uint64_t wb = (nanbits >> o) & ((1ull << NT) - 1ull);
-                if (wb != 0) {
-                    const double bot = smooth_bot_with_nans<H>(sm.taps, wb, p.ksum, p.ntaps);
-                    res[o] = (bot == 0.0) ? (double)centre_filled[o] : res[o] / bot;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < B; ++o) {
-            const int64_t c = c0 + o;
-            if (interior || c < p.nchan) {                           // uniform
-                if (EPI == 0) {
-                    if (active) *reinterpret_cast<float *>(outp) = (float)res[o];
-                    outp += out_step;
-                } else if (EPI == 1) {
-                    if (active) *reinterpret_cast<double *>(outp) = res[o];
-                    outp += out_step;
-                } else {
-                    // fused moments: the smoothed value enters as the materialised dtype would hold it,
-                    // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
-                    const double sv = p.round_f32 ? (double)(float)res[o] : res[o];
-                    const bool inc = ((incbits >> (o + H)) & 1ull) && sv == sv;
-                    if (inc) {
-                        const double2 t = __ldg(p.tab + c);
-                        s0 += sv;
-                        s1 = fma(sv, t.x, s1);
-                        s2 = fma(sv, t.y, s2);
-                        cnt += 1;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (i >= 1 && lane == 0) mbar_arrive(&sm.empty[sprev]);
-        sprev = scur; scur = snext; snext = (snext + 1 == STAGES) ? 0 : snext + 1;
+    for (int q = 0; q < 2 * H; ++q) {
+        car[q] = 0.0;
+        if (q >= H)
+            car[q] = smooth_take<MODE, EPI, bits_t>(p, sm.data[0][q - H][tid], q - H < p.nchan, q, q - H, y, x, nanbits, incbits, any_included);
     }
+
+    int scur = 0, snext = 1 % STAGES;
+    for (int i = 0; i < nblk; ++i) {
+        if (warp == 0) {
+            const int j = i + STAGES - 1;
+            if (j < nblk) {
+                if (i >= 1) mbar_wait(&sm.empty[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
+                issue_block(j);
+            }
+        }
+        if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
+        smooth_block<H, MODE, EPI, bits_t, 2 * H>(p, sm, car, 0, cur, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
+                                                  (int64_t)i * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
+        // slide the window by B channels (register moves; the compiler renames most of them away)
+#pragma unroll
+        for (int q = 0; q < 2 * H; ++q) car[q] = (q + B < 2 * H) ? car[q + B] : cur[q + B - 2 * H];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[scur]);                 // rows [H, B) of `next` are read next round
+        scur = snext; snext = (snext + 1 == STAGES) ? 0 : snext + 1;
+    }
+
     if (EPI != 2 && MODE != MODE_NONE && p.passthrough_spaxels && active && !any_included) {
         // `_apply_spectral_function` (spectral_cube.py:147-158): a spaxel with nothing included is
         // copied through (= the fill value everywhere).  Away from the spectral edges the convolution
@@ -244,15 +346,15 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     }
     if (EPI == 2 && active) {
         const int64_t o = y * p.nx + x;
-        const bool any = cnt > 0;
-        const double mean = s1 / s0;
-        if (p.m0) p.m0[o] = any ? s0 * p.pix_size : nan64();
+        const bool any = acc.cnt > 0;
+        const double mean = acc.s1 / acc.s0;
+        if (p.m0) p.m0[o] = any ? acc.s0 * p.pix_size : nan64();
         if (p.m1) p.m1[o] = any ? (p.K + mean) + p.m1_offset : nan64();
-        if (p.m2) p.m2[o] = any ? ((cnt == 1 && s0 != 0.0) ? 0.0 : s2 / s0 - mean * mean) : nan64();
+        if (p.m2) p.m2[o] = any ? ((acc.cnt == 1 && acc.s0 != 0.0) ? 0.0 : acc.s2 / acc.s0 - mean * mean) : nan64();
     }
 }
 
-// ---- generic fallback: any tap count, any alignment; one thread per output voxel column ----------
+// ---- generic fallback: any tap count, any alignment; one thread per spaxel ---------------------------
 template <int MODE, int EPI>
 __global__ void __launch_bounds__(128)
 smooth_generic_kernel(const __grid_constant__ SmoothParams p, const double *__restrict__ taps, int ntaps) {
@@ -309,10 +411,10 @@ smooth_generic_kernel(const __grid_constant__ SmoothParams p, const double *__re
 __global__ void moment_table_kernel(const double *__restrict__ x, int64_t n, double K, double2 *tab);
 
 // ---- launch plumbing ---------------------------------------------------------------------------
-template <int H, int B, int STAGES, int MODE, int EPI>
+template <int H, int MODE, int EPI>
 static cudaError_t launch_smooth_one(const SmoothParams &p, unsigned grid, cudaStream_t s) {
-    auto kern = smooth_tma_kernel<H, B, STAGES, MODE, EPI>;
-    const size_t smem = sizeof(SmoothSmem<B, STAGES>);
+    auto kern = smooth_tma_kernel<H, MODE, EPI>;
+    const size_t smem = sizeof(SmoothSmem);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -323,29 +425,37 @@ static cudaError_t launch_smooth_one(const SmoothParams &p, unsigned grid, cudaS
     return cudaGetLastError();
 }
 
-template <int H, int B, int STAGES, int EPI>
+// kernel-side mask mode: the interval form is only used when the fill value is NaN
+static int smooth_mode(const SmoothParams &p) {
+    if (p.mask.mode == MODE_INTERVAL && p.fill == p.fill) return MODE_GENERIC;
+    return p.mask.mode;
+}
+
+template <int H, int EPI>
 static cudaError_t launch_smooth_mode(const SmoothParams &p, unsigned grid, cudaStream_t s) {
-    switch (p.mask.mode) {
-        case MODE_NONE:     return launch_smooth_one<H, B, STAGES, MODE_NONE, EPI>(p, grid, s);
-        case MODE_INTERVAL: return launch_smooth_one<H, B, STAGES, MODE_INTERVAL, EPI>(p, grid, s);
-        default:            return launch_smooth_one<H, B, STAGES, MODE_GENERIC, EPI>(p, grid, s);
+    switch (smooth_mode(p)) {
+        case MODE_NONE:     return launch_smooth_one<H, MODE_NONE, EPI>(p, grid, s);
+        case MODE_INTERVAL: return launch_smooth_one<H, MODE_INTERVAL, EPI>(p, grid, s);
+        default:            return launch_smooth_one<H, MODE_GENERIC, EPI>(p, grid, s);
     }
 }
 
+static int padded_half(int h) { return h <= 2 ? 2 : h <= 4 ? 4 : h <= 8 ? 8 : 16; }
+
 template <int EPI>
 static cudaError_t launch_smooth_h(const SmoothParams &p, int h, unsigned grid, cudaStream_t s) {
-    if (h <= 2)  return launch_smooth_mode<2, 16, 5, EPI>(p, grid, s);
-    if (h <= 4)  return launch_smooth_mode<4, 16, 5, EPI>(p, grid, s);
-    if (h <= 6)  return launch_smooth_mode<6, 16, 5, EPI>(p, grid, s);
-    if (h <= 8)  return launch_smooth_mode<8, 16, 5, EPI>(p, grid, s);
-    if (h <= 12) return launch_smooth_mode<12, 16, 5, EPI>(p, grid, s);
-    return launch_smooth_mode<16, 16, 5, EPI>(p, grid, s);
+    switch (padded_half(h)) {
+        case 2:  return launch_smooth_mode<2, EPI>(p, grid, s);
+        case 4:  return launch_smooth_mode<4, EPI>(p, grid, s);
+        case 8:  return launch_smooth_mode<8, EPI>(p, grid, s);
+        default: return launch_smooth_mode<16, EPI>(p, grid, s);
+    }
 }
 
 template <int EPI>
 static cudaError_t launch_generic(const SmoothParams &p, const double *taps_dev, int ntaps, cudaStream_t s) {
     const unsigned grid = (unsigned)cdiv(p.ny * p.nx, 128);
-    switch (p.mask.mode) {
+    switch (smooth_mode(p)) {
         case MODE_NONE:     smooth_generic_kernel<MODE_NONE, EPI><<<grid, 128, 0, s>>>(p, taps_dev, ntaps); break;
         case MODE_INTERVAL: smooth_generic_kernel<MODE_INTERVAL, EPI><<<grid, 128, 0, s>>>(p, taps_dev, ntaps); break;
         default:            smooth_generic_kernel<MODE_GENERIC, EPI><<<grid, 128, 0, s>>>(p, taps_dev, ntaps); break;
@@ -367,9 +477,12 @@ static int prepare_taps(const double *taps, int ntaps, SmoothParams &p, int *h_o
     p.ntaps = ntaps;
     p.ksum = ksum;
     if (h <= 16) {
-        const int H = h <= 2 ? 2 : h <= 4 ? 4 : h <= 6 ? 6 : h <= 8 ? 8 : h <= 12 ? 12 : 16;
-        for (int k = 0; k < SM_MAX_TAPS; ++k) p.taps[k] = 0.0;
-        for (int k = 0; k < ntaps; ++k) p.taps[k + (H - h)] = norm[k];
+        const int H = padded_half(h);
+        for (int k = 0; k < SM_MAX_TAPS; ++k) { p.taps[k] = 0.0; p.taps_scaled[k] = 0.0; }
+        for (int k = 0; k < ntaps; ++k) {
+            p.taps[k + (H - h)] = norm[k];
+            p.taps_scaled[k + (H - h)] = ldexp(norm[k], 896);       // exact: undoes place_scaled's 2^-896
+        }
     }
     return SC_OK;
 }
@@ -384,6 +497,7 @@ static int run_smooth(SmoothParams &p, const sc_mask_desc *mask, const double *t
     if (rc) return rc;
     rc = build_dev_mask(mask, p.in, p.stride_c, p.stride_y, &p.mask);
     if (rc) return rc;
+    p.debug = env_int("SC_SMOOTH_DEBUG", 0);
     const bool aligned = ((uintptr_t)p.in % 16 == 0) && p.stride_c % 4 == 0 && p.stride_y % 4 == 0 && p.nx % 4 == 0;
     const int choice = env_int("SC_SMOOTH_KERNEL", 0);            // 0 auto, 1 generic, 2 tma
     const int64_t tiles_per_row = cdiv(p.nx, SM_TILE);

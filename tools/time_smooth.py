@@ -15,7 +15,7 @@ def timeit(f, n=5, warm=2):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
-which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+which = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
 if which in ('all', 'spectral'):
     nchan, ny, nx = 1024, 2048, 2048
     dev = synth_cube(nchan, ny, nx, border=51)
