@@ -52,6 +52,8 @@ struct SpatialParams {
     double ksum;                         // sum of the normalised 2-D kernel (~1)
     double ty[SP_MAX_TAPS], tx[SP_MAX_TAPS];     // normalised factors, centred in 2H+1, zero padded
     float tyf[SP_MAX_TAPS], txf[SP_MAX_TAPS];
+    double tx_scaled[SP_MAX_TAPS];        // tx * 2^896 (the row pass widens float32 by bit placement)
+    float lo_closed, hi_closed;          // interval mask as a closed float32 interval
     const uint8_t *passthrough;          // (nchan) 1 = copy the filled plane through; may be NULL
     DevMask mask;
 };
@@ -70,6 +72,15 @@ __device__ __forceinline__ bool mask_include_rt(const DevMask &m, float v, int64
     if (m.mode == MODE_NONE) return true;
     if (m.mode == MODE_INTERVAL) return (v > m.lo) & (v < m.hi);
     return eval_mask_generic(m.prog, v, c, y, x);
+}
+
+// v * 2^-896 as a double, exactly, for finite v (see spectral_smooth.cu); +-inf stays +-inf
+__device__ __forceinline__ double place_scaled_sp(float v) {
+    const int b = __float_as_int(v);
+    const long long t = (long long)b << 29;
+    int hi = (int)(t >> 32) & 0x8FFFFFFF;
+    if ((b & 0x7F800000) == 0x7F800000) hi |= 0x7FF00000;
+    return __hiloint2double(hi, (int)t);
 }
 
 __device__ __forceinline__ void compute_bar() {          // barrier among the SP_TX compute threads only
@@ -144,7 +155,13 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
     float bot_full = 0.0f;
 #pragma unroll
     for (int k = 0; k < NT; ++k) bot_full = fmaf(p.tyf[k], botx_full, bot_full);
+    // res = top / (ksum * bot / bot_full) = top * recip_scale * (1 / bot); the float reciprocal is widened
+    // by bit placement (x 2^-896), which recip_scale undoes
+    const double recip_scale = ((double)bot_full / p.ksum) * 0x1p+896;
     const bool pass = p.passthrough && p.passthrough[c];
+    const bool strip_clipped = xl != x0 - SP_HP || xr != x0 + SP_TX + SP_HP;
+    // masks that are not "closed interval with NaN fill" are applied by the in-place sweep
+    const bool mask_by_sweep = p.mask.mode == MODE_GENERIC || (p.mask.mode == MODE_INTERVAL && p.fill == p.fill);
 
     const int rrow = tid >> 4;            // row-pass mapping: row of the block
     const int roct = tid & 15;            // ... and octet of columns
@@ -154,64 +171,85 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
         const int64_t yblk = y_first + (int64_t)b * SP_R;
         mbar_wait(&sm.full[s], (b / SP_RS) & 1);
 
-        // (1) in place: zero what the copy did not cover, apply mask/fill to the cube's own rows
+        // (1) Only where needed (uniform per block): zero what the copy did not cover and apply masks that
+        //     the row pass cannot fold into its validity test.  Interior blocks skip this and its barrier.
+        const bool rows_inside = yblk >= (p.halo_top ? -(int64_t)p.halo_rows : 0) &&
+                                 yblk + SP_R <= p.ny + (p.halo_bot ? (int64_t)p.halo_rows : 0);
+        const bool sweep = strip_clipped || !rows_inside || mask_by_sweep;
+        float lo_c = -INFINITY, hi_c = INFINITY;                     // closed validity interval of the row pass
+        if (sweep) {
 #pragma unroll 1
-        for (int r = 0; r < SP_R; ++r) {
-            const int64_t y = yblk + r;                              // uniform
-            const bool own = y >= 0 && y < p.ny;
-            const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
-            const bool need_mask = own && p.mask.mode != MODE_NONE;
-            const bool all_valid = (own || halo) && xl == x0 - SP_HP && xr == x0 + SP_TX + SP_HP;
-            if (all_valid && !need_mask) continue;                   // the copy filled the whole row as is
-            for (int col = tid; col < SP_W; col += SP_TX) {
-                const int64_t x = x0 - SP_HP + col;
-                float v = 0.0f;                                      // outside the image: a valid zero
-                if (x >= xl && x < xr && (own || halo)) {
-                    v = sm.raw[s][r][col];
-                    if (need_mask && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+            for (int r = 0; r < SP_R; ++r) {
+                const int64_t y = yblk + r;                          // uniform
+                const bool own = y >= 0 && y < p.ny;
+                const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
+                const bool need_mask = own && p.mask.mode != MODE_NONE;
+                for (int col = tid; col < SP_W; col += SP_TX) {
+                    const int64_t x = x0 - SP_HP + col;
+                    float v = 0.0f;                                  // outside the image: a valid zero
+                    if (x >= xl && x < xr && (own || halo)) {
+                        v = sm.raw[s][r][col];
+                        if (need_mask && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+                    }
+                    sm.raw[s][r][col] = v;
                 }
-                sm.raw[s][r][col] = v;
             }
+            compute_bar();
+        } else if (p.mask.mode == MODE_INTERVAL) {
+            lo_c = p.lo_closed; hi_c = p.hi_closed;                  // excluded == NaN-filled == "missing"
         }
-        compute_bar();
 
         // (2) row pass: 8 adjacent outputs of row `rrow` from 40 aligned inputs
         {
             double w[NIN_X];
             float okf[NIN_X];
-            bool anynan = false;
+            bool anybad = false;
 #pragma unroll
             for (int q = 0; q < NIN_X / 4; ++q) {
                 const float4 f = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][roct * 8 + q * 4]);
                 const float a[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
                 for (int z = 0; z < 4; ++z) {
-                    const bool isn = a[z] != a[z];
-                    anynan |= isn;
-                    w[q * 4 + z] = isn ? 0.0 : (double)a[z];
-                    okf[q * 4 + z] = isn ? 0.0f : 1.0f;
+                    const bool ok = (a[z] >= lo_c) & (a[z] <= hi_c);  // false for NaN
+                    anybad |= !ok;
+                    w[q * 4 + z] = place_scaled_sp(ok ? a[z] : 0.0f);
+                    okf[q * 4 + z] = ok ? 1.0f : 0.0f;
                 }
             }
             const int slot = (b % NB) * SP_R + rrow;
+            double top[SP_R];
 #pragma unroll
-            for (int j = 0; j < SP_R; ++j) {
-                double top = 0.0;
+            for (int j = 0; j < SP_R; ++j) top[j] = 0.0;
 #pragma unroll
-                for (int k = 0; k < NT; ++k) top = fma(p.tx[k], w[j + SP_HP + H - k], top);
-                float bot = botx_full;
-                if (anynan) {
-                    bot = 0.0f;
+            for (int k = 0; k < NT; ++k) {                           // tap-outer: each tap is fetched once
+                const double t = p.tx_scaled[k];
 #pragma unroll
-                    for (int k = 0; k < NT; ++k) bot = fmaf(p.txf[k], okf[j + SP_HP + H - k], bot);
+                for (int j = 0; j < SP_R; ++j) top[j] = fma(t, w[j + SP_HP + H - k], top[j]);
+            }
+            float bot[SP_R];
+#pragma unroll
+            for (int j = 0; j < SP_R; ++j) bot[j] = botx_full;
+            if (anybad) {
+#pragma unroll
+                for (int j = 0; j < SP_R; ++j) bot[j] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const float t = p.txf[k];
+#pragma unroll
+                    for (int j = 0; j < SP_R; ++j) bot[j] = fmaf(t, okf[j + SP_HP + H - k], bot[j]);
                 }
-                sm.top[slot][roct * 8 + j] = top;
-                sm.bot[slot][roct * 8 + j] = bot;
+            }
+#pragma unroll
+            for (int j = 0; j < SP_R; j += 2) {
+                *reinterpret_cast<double2 *>(&sm.top[slot][roct * 8 + j]) = make_double2(top[j], top[j + 1]);
+                *reinterpret_cast<float2 *>(&sm.bot[slot][roct * 8 + j]) = make_float2(bot[j], bot[j + 1]);
             }
             // centre values (filled input) for the bot == 0 / pass-through cases
-            const float4 c0 = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][SP_HP + roct * 8]);
-            const float4 c1 = *reinterpret_cast<const float4 *>(&sm.raw[s][rrow][SP_HP + roct * 8 + 4]);
-            *reinterpret_cast<float4 *>(&sm.ctr[slot][roct * 8]) = c0;
-            *reinterpret_cast<float4 *>(&sm.ctr[slot][roct * 8 + 4]) = c1;
+#pragma unroll
+            for (int j = 0; j < SP_R; ++j) {
+                const float cv = sm.raw[s][rrow][SP_HP + roct * 8 + j];
+                sm.ctr[slot][roct * 8 + j] = ((cv >= lo_c) & (cv <= hi_c)) || cv != cv || sweep ? cv : p.fill;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
@@ -232,33 +270,39 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
             }
 #pragma unroll
             for (int i = 0; i < NIN_Y; ++i) {
-                // march-row jb*R - H + i, relative to the first row of block b - 2HB
-                constexpr int dummy = 0; (void)dummy;
-                const int rel = HB * SP_R - H + i;                   // compile-time
+                const int rel = HB * SP_R - H + i;                   // compile-time: row relative to block b - 2HB
                 const int slot = slot_of[rel / SP_R] + (rel % SP_R);
                 w[i] = sm.top[slot][tid];
                 bt[i] = sm.bot[slot][tid];
             }
             const int64_t x = x0 + tid;
+            double top[SP_R];
+            float bot[SP_R];
+#pragma unroll
+            for (int r = 0; r < SP_R; ++r) { top[r] = 0.0; bot[r] = 0.0f; }
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const double t = p.ty[k];
+                const float tf = p.tyf[k];
+#pragma unroll
+                for (int r = 0; r < SP_R; ++r) {
+                    top[r] = fma(t, w[r + 2 * H - k], top[r]);
+                    bot[r] = fmaf(tf, bt[r + 2 * H - k], bot[r]);
+                }
+            }
+            char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
+            const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
 #pragma unroll
             for (int r = 0; r < SP_R; ++r) {
-                const int64_t y = yout + r;
-                double top = 0.0;
-                float bot = 0.0f;
-#pragma unroll
-                for (int k = 0; k < NT; ++k) {
-                    top = fma(p.ty[k], w[r + 2 * H - k], top);
-                    bot = fmaf(p.tyf[k], bt[r + 2 * H - k], bot);
-                }
-                if (y < yb && x < p.nx) {
-                    const float centre = sm.ctr[slot_of[HB] + r][tid];
-                    double res;
-                    if (bot == bot_full) res = top;
-                    else if (bot == 0.0f) res = (double)centre;
-                    else res = top / (p.ksum * ((double)bot / (double)bot_full));
-                    if (pass) res = (double)centre;
-                    if (OUT64) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
-                    else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
+                if (yout + r < yb && x < p.nx) {
+                    double res = top[r];
+                    if (bot[r] != bot_full || pass) {
+                        const float centre = sm.ctr[slot_of[HB] + r][tid];
+                        if (bot[r] == 0.0f || pass) res = (double)centre;
+                        else res = top[r] * recip_scale * place_scaled_sp(__frcp_rn(bot[r]));
+                    }
+                    if (OUT64) *reinterpret_cast<double *>(op + r * ostep) = res;
+                    else       *reinterpret_cast<float *>(op + r * ostep) = (float)res;
                 }
             }
         }
@@ -441,7 +485,9 @@ extern "C" int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
         double ksy = 0.0, ksx = 0.0;
         for (int k = 0; k < SP_MAX_TAPS; ++k) { p.ty[k] = p.tx[k] = 0.0; p.tyf[k] = p.txf[k] = 0.0f; }
         for (int k = 0; k < ntaps_y; ++k) { p.ty[k + H - hy] = taps_y[k] / sy; ksy += p.ty[k + H - hy]; p.tyf[k + H - hy] = (float)p.ty[k + H - hy]; }
-        for (int k = 0; k < ntaps_x; ++k) { p.tx[k + H - hx] = taps_x[k] / sx; ksx += p.tx[k + H - hx]; p.txf[k + H - hx] = (float)p.tx[k + H - hx]; }
+        for (int k = 0; k < SP_MAX_TAPS; ++k) p.tx_scaled[k] = 0.0;
+        for (int k = 0; k < ntaps_x; ++k) { p.tx[k + H - hx] = taps_x[k] / sx; ksx += p.tx[k + H - hx]; p.txf[k + H - hx] = (float)p.tx[k + H - hx]; p.tx_scaled[k + H - hx] = ldexp(p.tx[k + H - hx], 896); }
+        p.lo_closed = nextafterf(p.mask.lo, INFINITY); p.hi_closed = nextafterf(p.mask.hi, -INFINITY);
         p.ksum = ksy * ksx;
         p.strips_per_row = (int)cdiv(nx, SP_TX);
         // row chunks: enough CTAs to fill the chip, each long enough to amortise the 2H-row run-in
