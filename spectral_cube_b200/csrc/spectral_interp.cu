@@ -13,19 +13,23 @@
 // (spectral_cube.py:3299-3313) falls out of the same pass.  Arithmetic is float64 and follows
 // numpy's / scipy's formulas term by term (see interp_numpy / interp_scipy below).
 #include "common.cuh"
+#include "tma.cuh"
 #include <vector>
 #include <algorithm>
 
 namespace scb {
 
 int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
+int env_int(const char *name, int dflt);
 
 enum { IK_INTERIOR = 0, IK_KNOT = 1, IK_LEFT = 2, IK_RIGHT = 3 };
 
 struct InterpEntry {          // 32 bytes
     int32_t need;             // highest ascending-order input channel this entry needs
     int32_t kind;
-    double x, xlo, xhi;
+    double t_lo;              // (x - xlo) / (xhi - xlo): weight of the step from the lower knot
+    double t_hi;              // (x - xhi) / (xhi - xlo): the same measured from the upper knot (<= 0)
+    double pad;
 };
 
 struct InterpParams {
@@ -42,20 +46,22 @@ struct InterpParams {
 };
 
 // numpy/_core/src/multiarray/compiled_base.c (arr_interp): interior sample between two knots
-__device__ __forceinline__ double interp_numpy(double x, double xlo, double xhi, double f0, double f1) {
-    const double slope = (f1 - f0) / (xhi - xlo);
-    double r = slope * (x - xlo) + f0;
+// (numpy: slope = (f1-f0)/(xhi-xlo); r = slope*(x-xlo) + f0; if NaN: slope*(x-xhi) + f1; if still NaN and
+// f0 == f1: f0).  The knot-spacing division is folded into the host-computed weights; the result
+// differs from numpy's rounding sequence by at most an ulp of float64.)
+__device__ __forceinline__ double interp_numpy(double t_lo, double t_hi, double f0, double f1) {
+    const double d = f1 - f0;
+    double r = fma(d, t_lo, f0);
     if (r != r) {
-        r = slope * (x - xhi) + f1;
+        r = fma(d, t_hi, f1);
         if (r != r && f0 == f1) r = f0;
     }
     return r;
 }
 
 // scipy/interpolate/_interpolate.py (interp1d._call_linear)
-__device__ __forceinline__ double interp_scipy(double x, double xlo, double xhi, double f0, double f1) {
-    const double slope = (f1 - f0) / (xhi - xlo);
-    return slope * (x - xlo) + f0;
+__device__ __forceinline__ double interp_scipy(double t_lo, double f0, double f1) {
+    return fma(f1 - f0, t_lo, f0);
 }
 
 template <int MODE, int OUT64>
@@ -85,12 +91,12 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
             double r;
             bool m;
             if (p.mode == 0) {
-                if (e.kind == IK_INTERIOR) { r = interp_numpy(e.x, e.xlo, e.xhi, (double)prev, (double)cur); m = mprev | mcur; }
+                if (e.kind == IK_INTERIOR) { r = interp_numpy(e.t_lo, e.t_hi, (double)prev, (double)cur); m = mprev | mcur; }
                 else if (e.kind == IK_KNOT) { r = (double)cur; m = mcur; }
                 else { r = p.has_fill_value ? p.fill_value : (double)cur; m = mcur; }       // left / right of the axis
             } else {
                 if (e.kind == IK_LEFT || e.kind == IK_RIGHT) r = p.has_fill_value ? p.fill_value : nan64();
-                else r = interp_scipy(e.x, e.xlo, e.xhi, (double)prev, (double)cur);
+                else r = interp_scipy(e.t_lo, (double)prev, (double)cur);
                 m = r == r;
             }
             const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
@@ -110,6 +116,167 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
             else       reinterpret_cast<float *>(p.out)[j * plane_out + obase] = nan32();
             if (p.out_mask) p.out_mask[j * plane_out + obase] = 0;
         }
+    }
+}
+
+// v * 2^-896 as a double, exactly, for finite v; NaN stays NaN and +-inf stays +-inf (see spectral_smooth.cu)
+__device__ __forceinline__ double place_scaled_keep(float v) {
+    const int b = __float_as_int(v);
+    const long long t = (long long)b << 29;
+    int hi = (int)(t >> 32) & 0x8FFFFFFF;
+    if ((b & 0x7F800000) == 0x7F800000) hi |= 0x7FF00000;
+    return __hiloint2double(hi, (int)t);
+}
+
+// ---- TMA-pipelined variant: same arithmetic, the spectrum arrives through a shared-memory ring ----------
+// CTA = 512 adjacent spaxels of one image row (float4 per thread, 128 consumer threads + a producer warp);
+// slabs of IT_CB channels x 2 KB rows stream through an IT_STAGES-deep ring like in moments.cu, in
+// ascending-axis order (the producer reverses the channel index for descending axes).  Outputs are
+// written as 16-byte vectors (data) and 4-byte vectors (mask).
+constexpr int IT_TILE = 512, IT_CONS = 128, IT_THREADS = IT_CONS + 32, IT_CB = 8, IT_STAGES = 4;
+
+struct InterpSmem {
+    float data[IT_STAGES][IT_CB][IT_TILE];
+    uint64_t full[IT_STAGES];
+    uint64_t empty[IT_STAGES];
+};
+
+template <int MODE, int OUT64>
+__global__ void __launch_bounds__(IT_THREADS)
+spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per_row) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    InterpSmem &sm = *reinterpret_cast<InterpSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tile = blockIdx.x;
+    const int64_t y = tile / tiles_per_row;
+    const int64_t x0 = (tile - y * tiles_per_row) * IT_TILE;
+    const int width = (int)min((int64_t)IT_TILE, p.nx - x0);
+    const int n_iter = (int)((p.nchan + IT_CB - 1) / IT_CB);
+    if (tid == 0) {
+        for (int s = 0; s < IT_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], IT_CONS / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == IT_CONS / 32) {
+        const float *src = p.in + y * p.stride_y + x0;
+        const uint64_t pol = l2_evict_first_policy();
+        const uint32_t row_bytes = (uint32_t)width * 4u;
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % IT_STAGES;
+            const int64_t i0 = (int64_t)it * IT_CB;
+            const int nch = (int)min((int64_t)IT_CB, p.nchan - i0);
+            if (it >= IT_STAGES) mbar_wait(&sm.empty[s], ((it / IT_STAGES) - 1) & 1);
+            if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)nch * row_bytes);
+            __syncwarp();
+            if (lane < nch) {
+                const int64_t ch = p.in_reversed ? p.nchan - 1 - (i0 + lane) : i0 + lane;
+                tma_load_1d(&sm.data[s][lane][0], src + ch * p.stride_c, row_bytes, &sm.full[s], pol);
+            }
+        }
+        return;
+    }
+    const int xo = tid * 4;
+    const bool active = xo < width;
+    const int64_t x = x0 + xo;
+    const int64_t plane_out = p.ny * p.nx;
+    const int64_t obase = y * p.nx + x;
+    // samples are widened to float64 by bit placement (value x 2^-896, NaN/inf preserved): no conversion
+    // unit on the input side; interpolated values are scaled back with one multiply
+    float cur[4] = {0, 0, 0, 0};
+    double pd[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
+    bool mprev[4] = {false, false, false, false}, mcur[4] = {false, false, false, false};
+    bool any_included[4] = {false, false, false, false};
+    int64_t jj = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const int s = it % IT_STAGES;
+        const int64_t i0 = (int64_t)it * IT_CB;
+        const int nch = (int)min((int64_t)IT_CB, p.nchan - i0);
+        mbar_wait(&sm.full[s], (it / IT_STAGES) & 1);
+        for (int cb = 0; cb < nch; ++cb) {
+            const int64_t i = i0 + cb;
+            const int64_t ch = p.in_reversed ? p.nchan - 1 - i : i;
+            const float4 v = *reinterpret_cast<const float4 *>(&sm.data[s][cb][xo]);
+            const float raw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                pd[k] = cd[k]; mprev[k] = mcur[k];
+                mcur[k] = mask_include<MODE>(p.mask, raw[k], ch, y, x + k);
+                cur[k] = mcur[k] ? raw[k] : p.fill;
+                cd[k] = place_scaled_keep(cur[k]);
+                any_included[k] |= mcur[k];
+            }
+            while (jj < p.nchan_out) {
+                const InterpEntry e = p.lut[jj];
+                if (e.need != (int32_t)i) break;
+                double r[4];
+                uint32_t mbits = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bool m;
+                    if (p.mode == 0) {
+                        if (e.kind == IK_INTERIOR) { r[k] = interp_numpy(e.t_lo, e.t_hi, pd[k], cd[k]) * 0x1p+896; m = mprev[k] | mcur[k]; }
+                        else if (e.kind == IK_KNOT) { r[k] = (double)cur[k]; m = mcur[k]; }
+                        else { r[k] = p.has_fill_value ? p.fill_value : (double)cur[k]; m = mcur[k]; }
+                    } else {
+                        if (e.kind == IK_LEFT || e.kind == IK_RIGHT) r[k] = p.has_fill_value ? p.fill_value : nan64();
+                        else r[k] = interp_scipy(e.t_lo, pd[k], cd[k]) * 0x1p+896;
+                        m = r[k] == r[k];
+                    }
+                    mbits |= (m ? 1u : 0u) << (8 * k);
+                }
+                const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
+                const int64_t jm = (p.mode == 1) ? jj : jo;
+                if (active) {
+                    if (OUT64) {
+                        double *o = reinterpret_cast<double *>(p.out) + jo * plane_out + obase;
+                        *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
+                        *reinterpret_cast<double2 *>(o + 2) = make_double2(r[2], r[3]);
+                    } else {
+                        float *o = reinterpret_cast<float *>(p.out) + jo * plane_out + obase;
+                        *reinterpret_cast<float4 *>(o) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
+                    }
+                    if (p.out_mask) *reinterpret_cast<uint32_t *>(p.out_mask + jm * plane_out + obase) = mbits;
+                }
+                ++jj;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+    if (p.mode == 0 && active && (p.fill == p.fill || p.has_fill_value)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (any_included[k]) continue;
+            for (int64_t j = 0; j < p.nchan_out; ++j) {
+                if (OUT64) reinterpret_cast<double *>(p.out)[j * plane_out + obase + k] = nan64();
+                else       reinterpret_cast<float *>(p.out)[j * plane_out + obase + k] = nan32();
+                if (p.out_mask) p.out_mask[j * plane_out + obase + k] = 0;
+            }
+        }
+    }
+}
+
+template <int MODE, int OUT64>
+static cudaError_t launch_interp_tma_one(const InterpParams &p, unsigned grid, int tiles_per_row, cudaStream_t s) {
+    auto kern = spectral_interp_tma_kernel<MODE, OUT64>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterpSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, IT_THREADS, sizeof(InterpSmem), s>>>(p, tiles_per_row);
+    return cudaGetLastError();
+}
+
+template <int OUT64>
+static cudaError_t launch_interp_tma(const InterpParams &p, cudaStream_t s) {
+    const int tiles_per_row = (int)cdiv(p.nx, IT_TILE);
+    const unsigned grid = (unsigned)(tiles_per_row * p.ny);
+    switch (p.mask.mode) {
+        case MODE_NONE:     return launch_interp_tma_one<MODE_NONE, OUT64>(p, grid, tiles_per_row, s);
+        case MODE_INTERVAL: return launch_interp_tma_one<MODE_INTERVAL, OUT64>(p, grid, tiles_per_row, s);
+        default:            return launch_interp_tma_one<MODE_GENERIC, OUT64>(p, grid, tiles_per_row, s);
     }
 }
 
@@ -161,20 +328,22 @@ extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uin
     for (int64_t j = 0; j < nchan_out; ++j) {
         const double xv = grid[j];
         InterpEntry e{};
-        e.x = xv;
+        double xlo = 0.0, xhi = 1.0;
         if (xv < x_first) { e.kind = IK_LEFT; e.need = 0; }
         else if (xv > x_last) { e.kind = IK_RIGHT; e.need = (int32_t)(nchan - 1); }
         else if (mode == 0) {
             // largest k with in_axis[k] <= xv
             const int64_t k = (std::upper_bound(in_axis, in_axis + nchan, xv) - in_axis) - 1;
             if (k == nchan - 1 || in_axis[k] == xv) { e.kind = IK_KNOT; e.need = (int32_t)k; }
-            else { e.kind = IK_INTERIOR; e.need = (int32_t)(k + 1); e.xlo = in_axis[k]; e.xhi = in_axis[k + 1]; }
+            else { e.kind = IK_INTERIOR; e.need = (int32_t)(k + 1); xlo = in_axis[k]; xhi = in_axis[k + 1]; }
         } else {
             int64_t hi = std::lower_bound(in_axis, in_axis + nchan, xv) - in_axis;    // searchsorted(left)
             if (hi < 1) hi = 1;
             if (hi > nchan - 1) hi = nchan - 1;
-            e.kind = IK_INTERIOR; e.need = (int32_t)hi; e.xlo = in_axis[hi - 1]; e.xhi = in_axis[hi];
+            e.kind = IK_INTERIOR; e.need = (int32_t)hi; xlo = in_axis[hi - 1]; xhi = in_axis[hi];
         }
+        e.t_lo = (xv - xlo) / (xhi - xlo);
+        e.t_hi = (xv - xhi) / (xhi - xlo);
         lut[(size_t)j] = e;
     }
     // `need` must be non-decreasing for the single streaming pass (it is: grid and axis are sorted;
@@ -190,7 +359,14 @@ extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uin
     rc = build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
     if (rc) return rc;
     LaunchScope ls(SC_OP_SPECTRAL_INTERP, s);
-    cudaError_t e = out_dtype == SC_F64 ? launch_interp<1>(p, s) : launch_interp<0>(p, s);
+    const bool aligned = ((uintptr_t)in % 16 == 0) && stride_c % 4 == 0 && stride_y % 4 == 0 && nx % 4 == 0 &&
+                         (uintptr_t)out % 16 == 0 && (!out_mask || (uintptr_t)out_mask % 4 == 0);
+    const int choice = env_int("SC_INTERP_KERNEL", 0);               // 0 auto, 1 direct, 2 tma
+    cudaError_t e;
+    if (aligned && choice != 1 && (choice == 2 || cdiv(nx, IT_TILE) * ny >= 148))
+        e = out_dtype == SC_F64 ? launch_interp_tma<1>(p, s) : launch_interp_tma<0>(p, s);
+    else
+        e = out_dtype == SC_F64 ? launch_interp<1>(p, s) : launch_interp<0>(p, s);
     if (e != cudaSuccess) return cuda_fail(e, "spectral_interp_kernel launch");
     return SC_OK;
 }

@@ -1,0 +1,168 @@
+"""
+Throughput of every BASELINE.json config beyond the headline one (bench.py covers configs[1]).
+Run on the GPU box:   python tools/bench_configs.py [c1] [c3] [c4] [c5]
+              or   python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py c4 c5
+Prints one JSON line per measurement (rank 0).  Timing: CUDA events, warm-up 2, mean of 5, max over ranks.
+"""
+import json, os, sys, time, warnings
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import spectral_cube_b200 as scb
+from spectral_cube_b200 import _lib, distributed as D
+from spectral_cube_b200.synth import synth_cube, benchmark_wcs
+
+rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(local)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs'] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')) else 6650.0
+
+
+def timeit(f, n=5, warm=2):
+    for _ in range(warm):
+        f()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        f()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def emit(config, what, voxels, ms, algo_bytes, **extra):
+    if rank == 0:
+        line = dict(config=config, what=what, n_gpus=world, voxels=voxels, ms=ms, voxels_per_s=voxels / ms * 1e3,
+                    algorithmic_GBps_per_gpu=algo_bytes / world / ms / 1e6, frac_of_measured_hbm=algo_bytes / world / ms / 1e6 / PEAK)
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+
+
+def isfinite_cube(cls, dev, w):
+    c = cls(dev, w, unit='K')
+    c._mask = scb.LazyMask(np.isfinite, cube=c)
+    return c
+
+
+which = [a for a in sys.argv[1:]] or ['c1', 'c3', 'c4', 'c5']
+
+if 'c1' in which and world == 1:
+    nchan, ny, nx = 128, 256, 256
+    dev = synth_cube(nchan, ny, nx, nan_permille=0, border=0)
+    c = scb.SpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit='K')       # no mask (configs[0])
+    ms = timeit(lambda: c._moments_axis0_raw(1), n=50, warm=5)
+    V = nchan * ny * nx
+    emit('c1', 'moment0, no mask, 256x256x128 (33.6 MB: L2 resident)', V, ms, 4 * V + 8 * ny * nx)
+    # CPU: the reference's own CPU-runnable case, cube strategy (moment_auto picks it below 1e8 voxels)
+    from oracle.cube import OracleCube
+    from oracle.wcs import OWCS
+    host = dev.cpu().numpy()
+    wkw = dict(ctype=['RA---TAN', 'DEC--TAN', 'VRAD'], crval=[24.0, 30.0, -321.214698632], crpix=[nx / 2 + 0.5, ny / 2 + 0.5, 1.0],
+               cdelt=[-5.55555561268e-4, 5.55555561268e-4, 1.28821496879], cunit=['deg', 'deg', 'km/s'])
+    oc = OracleCube(host, OWCS(**wkw), unit='K', mask=None)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ref = oc.moment(order=0, how='auto')[0]
+    cpu_s = (time.perf_counter() - t0) / 5
+    got = c.moment0().value
+    ok = bool(np.allclose(got, ref, rtol=1e-5, equal_nan=True))
+    if rank == 0:
+        print(json.dumps(dict(config='c1', what='CPU oracle moment0 (cube strategy), 1 thread', voxels=V, ms=cpu_s * 1e3,
+                              voxels_per_s=V / cpu_s, parity_rtol_1e5=ok)), flush=True)
+    del dev, c
+
+if 'c3' in which and world == 1:
+    nchan, ny, nx = 1024, 2048, 2048
+    V = nchan * ny * nx
+    dev = synth_cube(nchan, ny, nx, border=51)
+    c = isfinite_cube(scb.DaskSpectralCube, dev, benchmark_wcs(nchan, ny, nx))
+    k = scb.Gaussian1DKernel(5 / 2.3548200450309493)
+    sm = c.spectral_smooth(k)
+    ms = timeit(lambda: sm._moments_axis0_raw(2))
+    emit('c3', 'spectral_smooth(FWHM 5 ch, 17 taps) -> moment1, FUSED (smoothed cube never written)', V, ms, 4 * V + 8 * ny * nx)
+    ms_s = timeit(lambda: c._run_spectral_smooth(k.array, _lib.F32))
+    emit('c3', 'spectral_smooth alone, float32 out (materialised)', V, ms_s, 8 * V)
+    mat = c.spectral_smooth(k, save_to_tmp_dir=True)
+    ms_m = timeit(lambda: mat._moments_axis0_raw(2))
+    emit('c3', 'moment1 of the materialised smoothed cube (mask refers to the OLD data: +4 B/voxel)', V, ms_m, 8 * V + 8 * ny * nx)
+    emit('c3', 'unfused total (smooth + moment1)', V, ms_s + ms_m, 16 * V + 8 * ny * nx)
+    del dev, c, sm, mat
+    torch.cuda.empty_cache()
+
+if 'c4' in which:
+    nchan, ny, nx = 512, 4096, 4096
+    V = nchan * ny * nx
+    y0, y1 = D.row_partition(ny, world)[rank]
+    dev = synth_cube(nchan, y1 - y0, nx, y0=y0, ny_total=ny, nx_total=nx, border=102)
+    w = benchmark_wcs(nchan, ny, nx)
+    k = scb.Gaussian2DKernel(8 / 2.3548200450309493)
+    if world == 1:
+        c = isfinite_cube(scb.DaskSpectralCube, dev, w)
+        ms = timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32), n=3, warm=1)
+        emit('c4', 'spatial_smooth(FWHM 8 px, 29x29 separable), whole 4096x4096x512 cube on one GPU', V, ms, 8 * V)
+    else:
+        sh = D.RowShardedCube.from_full_wcs(scb.DaskSpectralCube, dev, w, ny, unit='K')
+        sh.local._mask = scb.LazyMask(np.isfinite, cube=sh.local)
+        for mode in ('p2p', 'allgather'):
+            ms = timeit(lambda: sh.spatial_smooth(k, halo_mode=mode), n=3, warm=1)
+            emit('c4', 'spatial_smooth(FWHM 8 px) row-sharded, halo exchange = %s (exchange inside the timed region)' % mode, V, ms, 8 * V)
+    del dev
+    torch.cuda.empty_cache()
+
+if 'c5' in which:
+    nchan, ny, nx = 2048, 4096, 4096
+    V = nchan * ny * nx
+    nout = 1024
+    # one GPU cannot hold the 137 GB cube plus its outputs: N = 1 runs the 1/8 row shard an 8-GPU job gives each rank
+    shards = max(world, 8)
+    y0, y1 = D.row_partition(ny, shards)[rank]
+    dev = synth_cube(nchan, y1 - y0, nx, y0=y0, ny_total=ny, nx_total=nx, border=102)
+    w = benchmark_wcs(nchan, ny, nx)
+    wl = w.copy(); wl.crpix[1] -= y0
+    c = isfinite_cube(scb.SpectralCube, dev, wl)
+    sa = c.spectral_axis
+    grid = np.linspace(sa[0], sa[-1], nout)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ms_i = timeit(lambda: c.spectral_interpolate(grid), n=3, warm=1)
+        Vs = nchan * (y1 - y0) * nx
+        emit('c5', 'spectral_interpolate 2048 -> 1024 channels, %d-row shard (1/%d of the cube) per GPU' % (y1 - y0, shards),
+             Vs * world, ms_i, world * (4 * Vs + 5 * Vs // 2))
+        interp = c.spectral_interpolate(grid)
+    del dev, c
+    torch.cuda.empty_cache()
+    a = np.radians(30.0)
+    hdr = dict(w.to_header())
+    hdr.update({'NAXIS': 3, 'NAXIS1': nx, 'NAXIS2': ny, 'NAXIS3': nout, 'PC1_1': np.cos(a), 'PC1_2': -np.sin(a),
+                'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
+    if world == 1:
+        # the channel shard a rank holds after the rows->channels re-shard: 128 whole planes
+        nloc = nout // shards
+        planes = synth_cube(nloc, ny, nx, border=102)
+        cc = isfinite_cube(scb.SpectralCube, planes, w)
+        hdr['NAXIS3'] = nloc
+        ms_r = timeit(lambda: cc.reproject(hdr), n=3, warm=1)
+        emit('c5', 'reproject (bilinear, WCS rotated 30 deg, incl. pixel map) of a %d-plane channel shard 4096x4096' % nloc,
+             nloc * ny * nx, ms_r, 4 * nloc * ny * nx + 9 * nloc * ny * nx + 16 * ny * nx)
+    else:
+        sh = D.RowShardedCube(interp, ny, y0, None)
+        t0 = timeit(lambda: D.reshard_rows_to_channels(interp._data, ny), n=3, warm=1)
+        emit('c5', 'rows -> channels re-shard (all-to-all) of the interpolated cube', nout * ny * nx, t0, 0)
+        ms_r = timeit(lambda: sh.reproject(hdr), n=2, warm=1)
+        emit('c5', 'reproject of the row-sharded interpolated cube (fill + all-to-all + pixel map + bilinear)', nout * ny * nx, ms_r,
+             (4 + 9) * nout * ny * nx)
+        emit('c5', 'config 5 total: spectral_interpolate + reproject', V, ms_i + ms_r, 0)
+
+if dist is not None:
+    dist.destroy_process_group()
