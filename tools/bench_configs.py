@@ -125,7 +125,7 @@ if 'c5' in which:
     V = nchan * ny * nx
     nout = 1024
     # one GPU cannot hold the 137 GB cube plus its outputs: N = 1 runs the 1/8 row shard an 8-GPU job gives each rank
-    shards = max(world, 8)
+    shards = world if world >= 4 else 8        # fewer than 4 GPUs cannot hold the whole cube: time one of 8 shards
     y0, y1 = D.row_partition(ny, shards)[rank]
     dev = synth_cube(nchan, y1 - y0, nx, y0=y0, ny_total=ny, nx_total=nx, border=102)
     w = benchmark_wcs(nchan, ny, nx)
@@ -146,7 +146,8 @@ if 'c5' in which:
     hdr = dict(w.to_header())
     hdr.update({'NAXIS': 3, 'NAXIS1': nx, 'NAXIS2': ny, 'NAXIS3': nout, 'PC1_1': np.cos(a), 'PC1_2': -np.sin(a),
                 'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
-    if world == 1:
+    if world < 4:
+      if world == 1:
         # the channel shard a rank holds after the rows->channels re-shard: 128 whole planes
         nloc = nout // shards
         planes = synth_cube(nloc, ny, nx, border=102)
