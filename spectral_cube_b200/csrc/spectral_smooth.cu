@@ -8,9 +8,10 @@
 // denominator 0 keeps the input value.  Masked voxels are replaced by `fill` before convolving.
 //
 // Kernel (smooth_tma_kernel).  A CTA owns SM_TILE adjacent spaxels of one image row, one per
-// thread.  Warp 0 streams blocks of B channels x SM_TILE floats (one `cp.async.bulk` / TMA row
-// copy of 1 KB per channel) through a STAGES-deep shared-memory ring guarded by full/empty
-// mbarriers, keeping STAGES-2 blocks in flight ahead of the arithmetic.  Per block of B output
+// thread.  Blocks of B channels x SM_TILE floats (one `cp.async.bulk` / TMA row copy of 1 KB per
+// channel) stream through a STAGES-deep shared-memory ring; arrival is an mbarrier per slot, and
+// the warp that is LAST to finish with a slot refills it at once (no producer role: a producer
+// that also computes paces the whole CTA, see the kernel).  Per block of B output
 // channels a thread
 //   * takes its B NEW inputs from the ring (every sample is loaded from shared memory, masked
 //     and widened to float64 exactly once; the 2H older inputs it still needs stay in registers:
@@ -44,6 +45,7 @@ constexpr int SM_MAX_TAPS = 2 * 16 + 1;
 constexpr int SM_LUT_CHUNKS = (SM_MAX_TAPS + 5) / 6;
 constexpr int SM_B = 16;                     // output channels per block
 constexpr int SM_STAGES = 6;
+constexpr int SM_G = 8;                      // outputs whose chains run side by side (register budget)
 
 struct SmoothParams {
     const float *in;
@@ -70,9 +72,10 @@ struct SmoothSmem {
     float data[SM_STAGES][SM_B][SM_TILE];
     double taps[SM_MAX_TAPS];
     double lut[SM_LUT_CHUNKS][64];           // lut[ch][m] = sum of taps whose window bits (6 ch + b) are set in m
-    double rlut1[SM_MAX_TAPS];               // rlut1[j] = 1 / (sum of all taps but the one under window bit j)
+    double tmul[SM_MAX_TAPS + 2 * SM_B];     // tmul[B + j] = 1 / (sum of all taps but the one under window bit j), 1 outside [0, 2H]
+    int rmul_degenerate;                     // some such sum is 0: the exact path handles every window with a NaN
     uint64_t full[SM_STAGES];
-    uint64_t empty[SM_STAGES];
+    unsigned int done[SM_STAGES];            // warps that have finished with the block in the slot
 };
 
 // v * 2^-896 as a double, exactly, for every finite v (zeros and denormals included): the float's
@@ -101,24 +104,28 @@ __device__ __forceinline__ double smooth_bot_present(const double (*lut)[64], ui
 
 // In the smoothing kernels MODE_INTERVAL means "interval mask AND the fill value is NaN" (the host
 // sends finite fills to MODE_GENERIC), so "excluded" and "NaN" collapse into one test.
-template <int MODE, int EPI, typename bits_t>
+// TAIL = false: the caller guarantees the channel exists (`valid` is ignored and folds away).
+template <int MODE, int EPI, bool TAIL, typename bits_t>
 __device__ __forceinline__ double smooth_take(const SmoothParams &p, float v, bool valid, int q, int64_t cc, int64_t y, int64_t x,
                                               bits_t &nanbits, bits_t &incbits, bool &any_included) {
     // `valid` (uniform): the channel exists; beyond the cube the sample is a VALID zero that no mask touches
+    constexpr bool TRACK_ANY = TAIL || MODE != MODE_INTERVAL;        // full INTERVAL blocks derive it from nanbits
+    const bits_t bit = (bits_t)1 << q;
     if (MODE == MODE_INTERVAL) {
         const bool inr = (v > p.mask.lo) & (v < p.mask.hi);
-        const bool use = inr & valid;                    // a real, included, finite sample
-        if (EPI == 2) incbits |= (bits_t)(use ? 1u : 0u) << q;
-        else any_included |= use;
-        nanbits |= (bits_t)((inr | !valid) ? 0u : 1u) << q;
+        const bool use = TAIL ? (inr & valid) : inr;                 // a real, included, finite sample
+        if (EPI == 2) { if (use) incbits |= bit; }
+        else if (TRACK_ANY) any_included |= use;
+        if (!(TAIL ? (inr | !valid) : inr)) nanbits |= bit;
         return place_scaled<false>(use ? v : 0.0f);
     }
-    const bool inc = valid && mask_include<MODE>(p.mask, v, cc, y, x);
-    if (EPI == 2) incbits |= (bits_t)((inc && v == v) ? 1u : 0u) << q;
+    const bool ok = TAIL ? valid : true;
+    const bool inc = ok && mask_include<MODE>(p.mask, v, cc, y, x);
+    if (EPI == 2) { if (inc && v == v) incbits |= bit; }
     else if (MODE != MODE_NONE) any_included |= inc;
-    v = valid ? (inc ? v : p.fill) : 0.0f;
+    v = ok ? (inc ? v : p.fill) : 0.0f;
     const bool isn = v != v;
-    nanbits |= (bits_t)(isn ? 1u : 0u) << q;
+    if (isn) nanbits |= bit;
     return place_scaled<true>(isn ? 0.0f : v);
 }
 
@@ -141,9 +148,78 @@ __device__ __noinline__ double smooth_fix(const SmoothParams &p, const SmoothSme
     return (double)cv;
 }
 
-// One block of B outputs.  `car` = the 2H inputs before this block's new ones (window entries
-// [0, 2H)), `cur` receives the B new inputs (entries [2H, 2H+B)).
-template <int H, int MODE, int EPI, typename bits_t, int NCAR>
+// Outputs [g, g + SM_G) of a block: window entry q is car[car_off + q] for q < 2H, cur[q - 2H] after.
+template <int H, int MODE, int EPI, bool TAIL, typename bits_t, int NCAR>
+__device__ __forceinline__ void smooth_emit(const SmoothParams &p, SmoothSmem &sm, const double (&car)[NCAR], int car_off,
+                                            const double (&cur)[SM_B], const float *pcur, int g,
+                                            int64_t c0, int64_t y, int64_t x, bool active,
+                                            bits_t nanbits, bits_t incbits, const double *tq, char *outp, int64_t out_step, SmoothAcc &acc) {
+    constexpr int NT = 2 * H + 1;
+    double res[SM_G];
+#pragma unroll
+    for (int oo = 0; oo < SM_G; ++oo) {
+        const int o = g + oo;
+        double top = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const int q = o + 2 * H - k;                         // out[c] += K[k] v[c + H - k]
+            top = fma(p.taps_scaled[k], q < 2 * H ? car[car_off + q] : cur[q - 2 * H], top);
+        }
+        res[oo] = top;
+    }
+    constexpr bits_t FULL = (bits_t)((1ull << NT) - 1ull);
+    constexpr bits_t GROUP = (bits_t)((1ull << (NT + SM_G - 1)) - 1ull);
+    if (((nanbits >> g) & GROUP) != 0) {
+        // Some inputs under these windows were NaN: rescale the outputs that saw one.  Usual case
+        // (`tq` set by the caller): the thread has ONE missing input, window entry Q, which sits under
+        // window bit Q - o of output o; the multiplier 1 / (sum of the other taps) is tmul[Q - o],
+        // padded with ones where the input is outside the window: one LDS + one DMUL per output.
+        // Several missing inputs (or a degenerate table): the exact path.
+        if (tq != nullptr) {
+#pragma unroll
+            for (int oo = 0; oo < SM_G; ++oo) res[oo] *= tq[-(g + oo)];
+        } else {
+#pragma unroll
+            for (int oo = 0; oo < SM_G; ++oo) {
+                const int o = g + oo;
+                const bits_t wb = (bits_t)(nanbits >> o) & FULL;
+                if (wb != 0) {
+                    if (MODE == MODE_INTERVAL && wb == FULL) res[oo] = (double)p.fill;   // nothing valid: the (NaN-filled) input
+                    else res[oo] = smooth_fix<H, MODE, bits_t>(p, sm, res[oo], wb, pcur + o * SM_TILE, !TAIL || c0 + o < p.nchan, c0 + o, y, x);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int oo = 0; oo < SM_G; ++oo) {
+        const int o = g + oo;
+        const int64_t c = c0 + o;
+        if (!TAIL || c < p.nchan) {                              // uniform
+            if (EPI == 0) {
+                if (active) *reinterpret_cast<float *>(outp + o * out_step) = (float)res[oo];
+            } else if (EPI == 1) {
+                if (active) *reinterpret_cast<double *>(outp + o * out_step) = res[oo];
+            } else {
+                // fused moments: the smoothed value enters as the materialised dtype would hold it,
+                // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
+                const double sv = p.round_f32 ? (double)(float)res[oo] : res[oo];
+                const bool inc = ((incbits >> (o + H)) & 1u) && sv == sv;
+                if (inc) {
+                    const double2 t = __ldg(p.tab + c);
+                    acc.s0 += sv;
+                    acc.s1 = fma(sv, t.x, acc.s1);
+                    acc.s2 = fma(sv, t.y, acc.s2);
+                    acc.cnt += 1;
+                }
+            }
+        }
+    }
+}
+
+// One block of B outputs.  `car` holds the 2H inputs before this block's new ones at
+// car[car_off .. car_off + 2H) (window entries [0, 2H)); `cur` receives the B new inputs
+// (entries [2H, 2H+B)).  TAIL = false: every channel this block reads or writes exists.
+template <int H, int MODE, int EPI, bool TAIL, typename bits_t, int NCAR>
 __device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &sm, const double (&car)[NCAR], int car_off,
                                              double (&cur)[SM_B], const float *pcur, const float *pnext,
                                              int64_t c0, int64_t y, int64_t x, bool active,
@@ -157,15 +233,17 @@ __device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &
         const int64_t cc = c0 + H + n;                           // uniform across the CTA
         // the ring row is always addressable; beyond the cube it holds stale bytes that `valid` discards
         const float v = (n < B - H) ? pcur[(n + H) * SM_TILE] : pnext[(n + H - B) * SM_TILE];
-        cur[n] = smooth_take<MODE, EPI, bits_t>(p, v, cc < p.nchan, q, cc, y, x, nanbits, incbits, any_included);
+        cur[n] = smooth_take<MODE, EPI, TAIL, bits_t>(p, v, TAIL ? cc < p.nchan : true, q, cc, y, x, nanbits, incbits, any_included);
     }
+    constexpr bits_t NEWBITS = (bits_t)((((bits_t)1 << B) - 1) << (2 * H));
+    if (!TAIL && MODE == MODE_INTERVAL && EPI != 2) any_included |= (nanbits & NEWBITS) != NEWBITS;
     // ---- blank spectra (every sample of every lane's window missing, e.g. the blanked frame of a mosaic):
     //      the result is the filled input itself, no arithmetic needed ----
     constexpr bits_t ALLBITS = (bits_t)(~(bits_t)0) >> (8 * sizeof(bits_t) - (B + 2 * H));
     if (EPI != 2 && __all_sync(0xffffffffu, nanbits == ALLBITS)) {
 #pragma unroll
         for (int o = 0; o < B; ++o) {
-            if (c0 + o < p.nchan && active) {
+            if ((!TAIL || c0 + o < p.nchan) && active) {
                 float cv = pcur[o * SM_TILE];
                 if (!mask_include<MODE>(p.mask, cv, c0 + o, y, x)) cv = p.fill;
                 if (EPI == 0) *reinterpret_cast<float *>(outp + o * out_step) = cv;
@@ -177,55 +255,16 @@ __device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &
         incbits >>= B;
         return;
     }
-    // ---- B independent n-tap chains; window entry q is car[car_off + q] for q < 2H, cur[q - 2H] after ----
-    double res[B];
-#pragma unroll
-    for (int o = 0; o < B; ++o) {
-        double top = 0.0;
-#pragma unroll
-        for (int k = 0; k < NT; ++k) {
-            const int q = o + 2 * H - k;                         // out[c] += K[k] v[c + H - k]
-            top = fma(p.taps_scaled[k], q < 2 * H ? car[car_off + q] : cur[q - 2 * H], top);
-        }
-        res[o] = top;
+    // ---- NaN bookkeeping: one missing input in the whole window -> table pointer, more -> exact path ----
+    const double *tq = nullptr;
+    if (nanbits != 0 && (nanbits & (nanbits - 1)) == 0 && !sm.rmul_degenerate) {
+        const int Q = (8 * (int)sizeof(bits_t) - 1) - (sizeof(bits_t) == 4 ? __clz((int)nanbits) : __clzll((long long)nanbits));
+        tq = &sm.tmul[Q + B];
     }
-    if (nanbits != 0) {
-        // some inputs were NaN: redo the denominator of the outputs whose window saw one
-        constexpr bits_t FULL = (bits_t)((1ull << NT) - 1ull);
+    // ---- the outputs, in groups of SM_G: SM_G independent n-tap chains, NaN fix-up, store ----
 #pragma unroll
-        for (int o = 0; o < B; ++o) {
-            const bits_t wb = (bits_t)(nanbits >> o) & FULL;
-            if (wb != 0) {
-                const int j = (8 * (int)sizeof(bits_t) - 1) - (sizeof(bits_t) == 4 ? __clz((int)wb) : __clzll((long long)wb));
-                const double r1 = sm.rlut1[j];
-                if ((wb & (wb - 1)) == 0 && r1 != 0.0) res[o] *= r1;      // one input missing: tabulated 1/bot
-                else res[o] = smooth_fix<H, MODE, bits_t>(p, sm, res[o], wb, pcur + o * SM_TILE, c0 + o < p.nchan, c0 + o, y, x);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < B; ++o) {
-        const int64_t c = c0 + o;
-        if (c < p.nchan) {                                       // uniform
-            if (EPI == 0) {
-                if (active) *reinterpret_cast<float *>(outp + o * out_step) = (float)res[o];
-            } else if (EPI == 1) {
-                if (active) *reinterpret_cast<double *>(outp + o * out_step) = res[o];
-            } else {
-                // fused moments: the smoothed value enters as the materialised dtype would hold it,
-                // under the include mask of the ORIGINAL data (spectral_cube.py:3043-3045)
-                const double sv = p.round_f32 ? (double)(float)res[o] : res[o];
-                const bool inc = ((incbits >> (o + H)) & 1u) && sv == sv;
-                if (inc) {
-                    const double2 t = __ldg(p.tab + c);
-                    acc.s0 += sv;
-                    acc.s1 = fma(sv, t.x, acc.s1);
-                    acc.s2 = fma(sv, t.y, acc.s2);
-                    acc.cnt += 1;
-                }
-            }
-        }
-    }
+    for (int g = 0; g < B; g += SM_G)
+        smooth_emit<H, MODE, EPI, TAIL, bits_t, NCAR>(p, sm, car, car_off, cur, pcur, g, c0, y, x, active, nanbits, incbits, tq, outp, out_step, acc);
     outp += B * out_step;
     nanbits >>= B;
     incbits >>= B;
@@ -238,6 +277,7 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     constexpr int B = SM_B, STAGES = SM_STAGES;
     constexpr int NT = 2 * H + 1;
     constexpr int NIN = B + 2 * H;
+    constexpr int NWARPS = SM_THREADS / 32;
     using bits_t = typename std::conditional<(NIN <= 32), uint32_t, uint64_t>::type;
     static_assert(H <= B, "window must fit in two neighbouring stages");
     static_assert(NIN <= 64, "NaN bit mask is 64 bits");
@@ -251,9 +291,12 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     const int64_t x0 = (tile - y * p.tiles_per_row) * SM_TILE;
     const int width = (int)min((int64_t)SM_TILE, p.nx - x0);
     const int nblk = (int)((p.nchan + B - 1) / B);
+    // blocks [0, nfull) touch existing channels only: (i + 1) B + H <= nchan
+    const int nfull = p.nchan >= H ? (int)((p.nchan - H) / B) : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SM_TILE / 32); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
+        sm.rmul_degenerate = 0;
         mbar_fence_init();
     }
     if (tid < NT) sm.taps[tid] = p.taps[tid];
@@ -267,15 +310,23 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
         }
         sm.lut[ch][m] = a;
     }
-    if (tid < NT) {
-        double a = 0.0;                                              // same summation order as the LUT path
-        for (int j = 0; j < NT; ++j) if (j != tid) a += sm.taps[2 * H - j];
-        sm.rlut1[tid] = a != 0.0 ? 1.0 / a : 0.0;
+    for (int u = tid; u < NT + 2 * B; u += SM_THREADS) {
+        const int t = u - B;                                         // window bit
+        double r = 1.0;
+        if (t >= 0 && t < NT) {
+            double a = 0.0;                                          // same summation order as the LUT path
+            for (int j = 0; j < NT; ++j) if (j != t) a += sm.taps[2 * H - j];
+            if (a != 0.0) r = 1.0 / a; else atomicOr(&sm.rmul_degenerate, 1);
+        }
+        sm.tmul[u] = r;
     }
     __syncthreads();
 
-    // Warp 0 doubles as the producer: block j is loaded into ring slot j % STAGES as soon as every warp
-    // has released the block that used the slot before (STAGES - 2 blocks stay in flight ahead of the math).
+    // Ring refill without a producer role: block j lives in slot j % STAGES.  Every warp bumps the
+    // slot's `done` counter when it has read the block; the warp that arrives LAST knows the slot is
+    // free and issues block j + STAGES into it at once.  (A fixed producer warp that also computes
+    // throttles the whole CTA to its own single-warp pace: the others run ahead, drain the ring and
+    // wait for it.)
     const float *gsrc = p.in + y * p.stride_y + x0;
     const uint64_t pol = l2_evict_first_policy();
     const uint32_t row_bytes = (uint32_t)width * 4u;
@@ -289,7 +340,7 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
             tma_load_1d(&sm.data[s][lane][0], gsrc + (cj + lane) * p.stride_c, row_bytes, &sm.full[s], pol);
     };
     if (warp == 0)
-        for (int j = 0; j < STAGES - 1 && j < nblk; ++j) issue_block(j);
+        for (int j = 0; j < STAGES && j < nblk; ++j) issue_block(j);
 
     const bool active = tid < width;
     const int64_t x = x0 + tid;
@@ -299,37 +350,71 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     const int64_t out_step = ((EPI == 1) ? 8 : 4) * p.out_stride_c;
     bits_t nanbits = 0, incbits = 0;
 
-    // window storage: the 2H carried inputs and the B new ones
-    double car[2 * H], cur[B];
+    // Window storage.  2H <= B: two B-entry arrays that swap roles block by block (the carried 2H
+    // inputs are simply the tail of the previous block's array: no register is moved).  2H > B:
+    // a 2H-entry carry array that is shifted by B after every block.
+    constexpr bool SWAP = 2 * H <= B;
+    constexpr int NCAR = SWAP ? B : 2 * H;
+    constexpr int CAR_OFF = SWAP ? B - 2 * H : 0;
+    double wa[NCAR], wb[B];
 
     // prologue: channels [-H, 0) are (valid) zeros, channels [0, H) come from the first stage; they
     // form window entries [0, 2H) of block 0
     mbar_wait(&sm.full[0], 0);
 #pragma unroll
     for (int q = 0; q < 2 * H; ++q) {
-        car[q] = 0.0;
+        wa[CAR_OFF + q] = 0.0;
         if (q >= H)
-            car[q] = smooth_take<MODE, EPI, bits_t>(p, sm.data[0][q - H][tid], q - H < p.nchan, q, q - H, y, x, nanbits, incbits, any_included);
+            wa[CAR_OFF + q] = smooth_take<MODE, EPI, true, bits_t>(p, sm.data[0][q - H][tid], q - H < p.nchan, q, q - H, y, x, nanbits, incbits, any_included);
     }
 
     int scur = 0, snext = 1 % STAGES;
-    for (int i = 0; i < nblk; ++i) {
-        if (warp == 0) {
-            const int j = i + STAGES - 1;
-            if (j < nblk) {
-                if (i >= 1) mbar_wait(&sm.empty[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
-                issue_block(j);
-            }
-        }
-        if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
-        smooth_block<H, MODE, EPI, bits_t, 2 * H>(p, sm, car, 0, cur, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
-                                                  (int64_t)i * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
-        // slide the window by B channels (register moves; the compiler renames most of them away)
-#pragma unroll
-        for (int q = 0; q < 2 * H; ++q) car[q] = (q + B < 2 * H) ? car[q + B] : cur[q + B - 2 * H];
+    // after a block: hand the slot back and, as the last warp to do so, refill it
+    auto release = [&](int i) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[scur]);                 // rows [H, B) of `next` are read next round
+        int last = 0;
+        // (no fence: the ring rows were consumed by arithmetic that precedes this point in issue order)
+        if (lane == 0) {
+            last = atomicAdd(&sm.done[scur], 1u) == (unsigned)(NWARPS - 1);
+            if (last) sm.done[scur] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && i + STAGES < nblk) issue_block(i + STAGES);
         scur = snext; snext = (snext + 1 == STAGES) ? 0 : snext + 1;
+    };
+
+    int i = 0;
+    if constexpr (SWAP) {
+        // pairs of full blocks: wa -> wb, then wb -> wa
+        for (; i + 2 <= nfull; i += 2) {
+            mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
+            smooth_block<H, MODE, EPI, false, bits_t, NCAR>(p, sm, wa, CAR_OFF, wb, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
+                                                            (int64_t)i * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
+            release(i);
+            if (i + 2 < nblk) mbar_wait(&sm.full[snext], ((i + 2) / STAGES) & 1);
+            smooth_block<H, MODE, EPI, false, bits_t, B>(p, sm, wb, B - 2 * H, wa, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
+                                                         (int64_t)(i + 1) * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
+            release(i + 1);
+        }
+    } else {
+        for (; i < nfull; ++i) {
+            if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
+            smooth_block<H, MODE, EPI, false, bits_t, NCAR>(p, sm, wa, CAR_OFF, wb, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
+                                                            (int64_t)i * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
+#pragma unroll
+            for (int q = 0; q < NCAR; ++q) wa[q] = (q + B < NCAR) ? wa[q + B] : wb[q + B - NCAR];
+            release(i);
+        }
+    }
+    // the remaining blocks (an odd full one, and those that run past the last channel)
+    for (; i < nblk; ++i) {
+        if (i + 1 < nblk) mbar_wait(&sm.full[snext], ((i + 1) / STAGES) & 1);
+        smooth_block<H, MODE, EPI, true, bits_t, NCAR>(p, sm, wa, CAR_OFF, wb, &sm.data[scur][0][tid], &sm.data[snext][0][tid],
+                                                       (int64_t)i * B, y, x, active, nanbits, incbits, any_included, outp, out_step, acc);
+        // slide the window by B channels
+#pragma unroll
+        for (int q = 0; q < NCAR; ++q) wa[q] = (q + B < NCAR) ? wa[q + B] : wb[q + B - NCAR];
+        release(i);
     }
 
     if (EPI != 2 && MODE != MODE_NONE && p.passthrough_spaxels && active && !any_included) {

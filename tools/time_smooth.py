@@ -18,7 +18,8 @@ def timeit(f, n=5, warm=2):
 which = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
 if which in ('all', 'spectral'):
     nchan, ny, nx = 1024, 2048, 2048
-    dev = synth_cube(nchan, ny, nx, border=51)
+    clean = os.environ.get('SC_BENCH_CLEAN') == '1'
+    dev = synth_cube(nchan, ny, nx, border=0, nan_permille=0) if clean else synth_cube(nchan, ny, nx, border=51)
     c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit='K')
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     vox = nchan * ny * nx
