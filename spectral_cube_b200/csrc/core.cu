@@ -1,5 +1,6 @@
 // core.cu -- library plumbing: error slot, launch accounting / per-op timing, mask classification.
 #include "common.cuh"
+#include "tma.cuh"
 #include <atomic>
 #include <string.h>
 #include <mutex>
@@ -33,6 +34,42 @@ void count_launch(int op, cudaStream_t s, bool begin) {
     if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
     if (begin) { cudaEventRecord(t.a, s); t.valid = false; }
     else       { cudaEventRecord(t.b, s); t.valid = true; }
+}
+
+// ---- tensor maps (TMA descriptors) -------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_cube_tensor_map(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
+                         int64_t stride_c, int64_t stride_y, int box_x, int box_c) {
+    static std::atomic<TensorMapEncodeFn> cached{nullptr};
+    TensorMapEncodeFn fn = cached.load(std::memory_order_acquire);
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !sym || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver (cudaGetDriverEntryPoint: %d)", (int)e);
+            return SC_ERR_CUDA;
+        }
+        fn = (TensorMapEncodeFn)sym;
+        cached.store(fn, std::memory_order_release);
+    }
+    // a one-row cube still needs a non-zero plane stride for the descriptor
+    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nchan};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride_y * 4u, (cuuint64_t)stride_c * 4u};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, 1u, (cuuint32_t)box_c};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld x %lld cube, strides %lld / %lld, box %d x %d",
+                  (int)r, (long long)nchan, (long long)ny, (long long)nx, (long long)stride_c, (long long)stride_y, box_x, box_c);
+        return SC_ERR_CUDA;
+    }
+    return SC_OK;
 }
 
 // ---- float32 thresholds equivalent to a float64 comparison -----------------------------------

@@ -48,6 +48,7 @@ constexpr int SM_STAGES = 6;
 constexpr int SM_G = 8;                      // outputs whose chains run side by side (register budget)
 
 struct SmoothParams {
+    alignas(64) CUtensorMap tmap;            // the input cube; box = {tile, 1, block channels}
     const float *in;
     void *out;                               // float32 or float64
     int64_t nchan, ny, nx;
@@ -58,7 +59,6 @@ struct SmoothParams {
     double ksum;                             // sum of the normalised taps (~1)
     double taps[SM_MAX_TAPS];                // normalised, centred in a 2H+1 window, zero padded
     double taps_scaled[SM_MAX_TAPS];         // the same times 2^896 (see place_scaled)
-    int debug;                               // experiments only: 1 = skip stores, 2 = skip the tap chains
     int passthrough_spaxels;                 // numpy class: spaxels with nothing included are copied through
     // fused moments
     const double2 *tab;                      // {d, d^2} per channel
@@ -131,21 +131,43 @@ __device__ __forceinline__ double smooth_take(const SmoothParams &p, float v, bo
 
 struct SmoothAcc { double s0, s1, s2; int cnt; };
 
-// Rare path, one copy in the binary: the window of this output saw missing (NaN) inputs; `wb` has
-// bit j set when window entry j is missing.  Returns top / bot, or the (filled) input value when
-// nothing under the kernel is valid.
+// Rare path, out of line (one copy per kernel, a rolled loop: the hot loop must stay small enough for
+// the instruction cache): the windows of a group of SM_G outputs saw several missing (NaN) inputs.
+// `nb` = nanbits >> g: bit j of (nb >> oo) is set when window entry j of output oo is missing.
+// res[oo] <- top / (sum of the present taps), or the (filled) input value when nothing under the
+// kernel is valid.  `centre` points at the ring sample of output 0 of the group (row stride SM_TILE);
+// outputs oo >= nvalid lie beyond the last channel.
 template <int H, int MODE, typename bits_t>
-__device__ __noinline__ double smooth_fix(const SmoothParams &p, const SmoothSmem &sm, double top, bits_t wb,
-                                          const float *centre, bool centre_valid, int64_t c, int64_t y, int64_t x) {
+__device__ __noinline__ void smooth_fix_group(const SmoothParams &p, const double (*lut)[64], double *res, bits_t nb,
+                                              const float *centre, int nvalid, int64_t c, int64_t y, int64_t x) {
     constexpr bits_t FULL = (bits_t)((1ull << (2 * H + 1)) - 1ull);
-    const double bot = wb == FULL ? 0.0 : smooth_bot_present<H>(sm.lut, (uint64_t)(bits_t)(~wb & FULL));
-    if (bot != 0.0) return top / bot;
-    float cv = 0.0f;                                             // nothing valid under the kernel
-    if (centre_valid) {
-        cv = *centre;
-        if (!mask_include<MODE>(p.mask, cv, c, y, x)) cv = p.fill;
+#pragma unroll 1
+    for (int oo = 0; oo < SM_G; ++oo) {
+        const bits_t wb = (bits_t)(nb >> oo) & FULL;
+        if (wb == 0) continue;
+        const double bot = wb == FULL ? 0.0 : smooth_bot_present<H>(lut, (uint64_t)(bits_t)(~wb & FULL));
+        if (bot != 0.0) { res[oo] = res[oo] / bot; continue; }
+        float cv = 0.0f;                                         // nothing valid under the kernel
+        if (oo < nvalid) {
+            cv = centre[oo * SM_TILE];
+            if (!mask_include<MODE>(p.mask, cv, c + oo, y, x)) cv = p.fill;
+        }
+        res[oo] = (double)cv;
     }
-    return (double)cv;
+}
+
+// Blank block, out of line: every sample of every lane's window is missing (the blanked frame of a
+// mosaic): the outputs are the filled inputs themselves.
+template <int MODE, int EPI>
+__device__ __noinline__ void smooth_blank_block(const SmoothParams &p, const float *pcur, char *outp, int64_t out_step,
+                                                int nvalid, int64_t c0, int64_t y, int64_t x) {
+#pragma unroll 1
+    for (int o = 0; o < nvalid; ++o) {
+        float cv = pcur[o * SM_TILE];
+        if (!mask_include<MODE>(p.mask, cv, c0 + o, y, x)) cv = p.fill;
+        if (EPI == 0) *reinterpret_cast<float *>(outp + o * out_step) = cv;
+        else          *reinterpret_cast<double *>(outp + o * out_step) = (double)cv;
+    }
 }
 
 // Outputs [g, g + SM_G) of a block: window entry q is car[car_off + q] for q < 2H, cur[q - 2H] after.
@@ -167,7 +189,6 @@ __device__ __forceinline__ void smooth_emit(const SmoothParams &p, SmoothSmem &s
         }
         res[oo] = top;
     }
-    constexpr bits_t FULL = (bits_t)((1ull << NT) - 1ull);
     constexpr bits_t GROUP = (bits_t)((1ull << (NT + SM_G - 1)) - 1ull);
     if (((nanbits >> g) & GROUP) != 0) {
         // Some inputs under these windows were NaN: rescale the outputs that saw one.  Usual case
@@ -178,16 +199,19 @@ __device__ __forceinline__ void smooth_emit(const SmoothParams &p, SmoothSmem &s
         if (tq != nullptr) {
 #pragma unroll
             for (int oo = 0; oo < SM_G; ++oo) res[oo] *= tq[-(g + oo)];
-        } else {
+        } else if (MODE != MODE_GENERIC && ((nanbits >> g) & GROUP) == GROUP) {
+            // every input under every window of the group is missing (a blank spaxel in a warp that
+            // also holds data): the output is the filled input, NaN in these two modes
 #pragma unroll
-            for (int oo = 0; oo < SM_G; ++oo) {
-                const int o = g + oo;
-                const bits_t wb = (bits_t)(nanbits >> o) & FULL;
-                if (wb != 0) {
-                    if (MODE == MODE_INTERVAL && wb == FULL) res[oo] = (double)p.fill;   // nothing valid: the (NaN-filled) input
-                    else res[oo] = smooth_fix<H, MODE, bits_t>(p, sm, res[oo], wb, pcur + o * SM_TILE, !TAIL || c0 + o < p.nchan, c0 + o, y, x);
-                }
-            }
+            for (int oo = 0; oo < SM_G; ++oo) res[oo] = nan64();
+        } else {
+            double tmp[SM_G];                                        // through local memory on this path only
+#pragma unroll
+            for (int oo = 0; oo < SM_G; ++oo) tmp[oo] = res[oo];
+            const int nvalid = TAIL ? (int)max((int64_t)0, min((int64_t)SM_G, p.nchan - (c0 + g))) : SM_G;
+            smooth_fix_group<H, MODE, bits_t>(p, sm.lut, tmp, (bits_t)(nanbits >> g), pcur + g * SM_TILE, nvalid, c0 + g, y, x);
+#pragma unroll
+            for (int oo = 0; oo < SM_G; ++oo) res[oo] = tmp[oo];
         }
     }
 #pragma unroll
@@ -241,15 +265,8 @@ __device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &
     //      the result is the filled input itself, no arithmetic needed ----
     constexpr bits_t ALLBITS = (bits_t)(~(bits_t)0) >> (8 * sizeof(bits_t) - (B + 2 * H));
     if (EPI != 2 && __all_sync(0xffffffffu, nanbits == ALLBITS)) {
-#pragma unroll
-        for (int o = 0; o < B; ++o) {
-            if ((!TAIL || c0 + o < p.nchan) && active) {
-                float cv = pcur[o * SM_TILE];
-                if (!mask_include<MODE>(p.mask, cv, c0 + o, y, x)) cv = p.fill;
-                if (EPI == 0) *reinterpret_cast<float *>(outp + o * out_step) = cv;
-                else          *reinterpret_cast<double *>(outp + o * out_step) = (double)cv;
-            }
-        }
+        if (active)
+            smooth_blank_block<MODE, EPI>(p, pcur, outp, out_step, TAIL ? (int)max((int64_t)0, min((int64_t)B, p.nchan - c0)) : B, c0, y, x);
         outp += B * out_step;
         nanbits >>= B;
         incbits >>= B;
@@ -274,7 +291,7 @@ __device__ __forceinline__ void smooth_block(const SmoothParams &p, SmoothSmem &
 template <int H, int MODE, int EPI>
 __global__ void __launch_bounds__(SM_THREADS, SM_MIN_CTAS)
 smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
-    constexpr int B = SM_B, STAGES = SM_STAGES;
+    constexpr int B = SM_B, STAGES = SM_STAGES, TILE_PX = SM_TILE;
     constexpr int NT = 2 * H + 1;
     constexpr int NIN = B + 2 * H;
     constexpr int NWARPS = SM_THREADS / 32;
@@ -327,17 +344,14 @@ smooth_tma_kernel(const __grid_constant__ SmoothParams p) {
     // free and issues block j + STAGES into it at once.  (A fixed producer warp that also computes
     // throttles the whole CTA to its own single-warp pace: the others run ahead, drain the ring and
     // wait for it.)
-    const float *gsrc = p.in + y * p.stride_y + x0;
+    // one tiled TMA request per ring slot (rows past the last channel / columns past nx arrive as zeros)
     const uint64_t pol = l2_evict_first_policy();
-    const uint32_t row_bytes = (uint32_t)width * 4u;
     auto issue_block = [&](int j) {
         const int s = j % STAGES;
-        const int64_t cj = (int64_t)j * B;
-        const int nch = (int)min((int64_t)B, p.nchan - cj);
-        if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)nch * row_bytes);
-        __syncwarp();
-        if (lane < nch)
-            tma_load_1d(&sm.data[s][lane][0], gsrc + (cj + lane) * p.stride_c, row_bytes, &sm.full[s], pol);
+        if (lane == 0) {
+            mbar_expect_tx(&sm.full[s], (uint32_t)(B * TILE_PX * 4));
+            tma_load_box3d(&sm.data[s][0][0], &p.tmap, (int)x0, (int)y, j * B, &sm.full[s], pol);
+        }
     };
     if (warp == 0)
         for (int j = 0; j < STAGES && j < nblk; ++j) issue_block(j);
@@ -582,7 +596,6 @@ static int run_smooth(SmoothParams &p, const sc_mask_desc *mask, const double *t
     if (rc) return rc;
     rc = build_dev_mask(mask, p.in, p.stride_c, p.stride_y, &p.mask);
     if (rc) return rc;
-    p.debug = env_int("SC_SMOOTH_DEBUG", 0);
     const bool aligned = ((uintptr_t)p.in % 16 == 0) && p.stride_c % 4 == 0 && p.stride_y % 4 == 0 && p.nx % 4 == 0;
     const int choice = env_int("SC_SMOOTH_KERNEL", 0);            // 0 auto, 1 generic, 2 tma
     const int64_t tiles_per_row = cdiv(p.nx, SM_TILE);
@@ -590,6 +603,9 @@ static int run_smooth(SmoothParams &p, const sc_mask_desc *mask, const double *t
     LaunchScope ls(op, s);
     if (h <= 16 && aligned && choice != 1 && n_tiles < ((int64_t)1 << 31)) {
         p.tiles_per_row = (int)tiles_per_row;
+        int trc = make_cube_tensor_map(&p.tmap, p.in, p.nchan, p.ny, p.nx, p.stride_c, p.stride_y,
+                                       SM_TILE, SM_B);
+        if (trc) return trc;
         cudaError_t e = launch_smooth_h<EPI>(p, h, (unsigned)n_tiles, s);
         if (e != cudaSuccess) return cuda_fail(e, "smooth_tma_kernel launch");
         return SC_OK;

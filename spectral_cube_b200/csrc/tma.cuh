@@ -4,6 +4,7 @@
 // phase parity and hand the stage back through a second ("empty") barrier.
 #pragma once
 #include <stdint.h>
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace scb {
 
@@ -57,6 +58,22 @@ __device__ __forceinline__ void tma_load_1d_nohint(void *smem_dst, const void *g
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// global -> shared TILED copy of one box {box_x, 1, box_c} of a (c, y, x) float32 cube described by a
+// tensor map (SASS: UTMALDG): ONE instruction per ring slot whatever the number of rows; elements
+// outside the cube arrive as zeros and still count towards the barrier's byte total.
+__device__ __forceinline__ void tma_load_box3d(void *smem_dst, const CUtensorMap *tmap, int x, int y, int c,
+                                               uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(c), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+// Host: describe a float32 cube view (element strides, x contiguous) and the box one request moves.
+// Needs base % 16 == 0, stride_y % 4 == 0, stride_c % 4 == 0, box_x % 4 == 0, box_x, box_c <= 256.
+int make_cube_tensor_map(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
+                         int64_t stride_c, int64_t stride_y, int box_x, int box_c);
 
 // shared -> global bulk store (bulk_group completion)
 __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
