@@ -319,13 +319,16 @@ class BaseSpectralCube(object):
         spectral_cube.py:3085/3139; the dask spectral path hard-codes NaN, dask:816-823)."""
         return self._fill_value
 
-    def _run_spectral_smooth(self, taps, out_dtype):
+    def _run_spectral_smooth(self, taps, out_dtype, out=None):
+        """`out` may be the cube's own float32 tensor: the kernel then smooths in place (a 137 GB
+        cube has no room for a second copy in 180 GB of HBM)."""
         torch = _torch()
         lib = _lib.load()
         src = self._data
         nchan, ny, nx = self.shape
-        out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
-                          device=src.device)
+        if out is None:
+            out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
+                              device=src.device)
         desc, keep = self._mask_desc()
         ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPECTRAL_SMOOTH, nchan, ny, nx, len(taps)))
         tarr, tptr = _lib.as_double_array(taps)

@@ -55,7 +55,7 @@ def isfinite_cube(cls, dev, w):
     return c
 
 
-which = [a for a in sys.argv[1:]] or ['c1', 'c3', 'c4', 'c5']
+which = [a for a in sys.argv[1:]] or ['c1', 'c3', 'c4', 'c5']      # 'target' (137 GB on one GPU) only on request
 
 if 'c1' in which and world == 1:
     nchan, ny, nx = 128, 256, 256
@@ -164,6 +164,28 @@ if 'c5' in which:
         emit('c5', 'reproject of the row-sharded interpolated cube (fill + all-to-all + pixel map + bilinear)', nout * ny * nx, ms_r,
              (4 + 9) * nout * ny * nx)
         emit('c5', 'config 5 total: spectral_interpolate + reproject', V, ms_i + ms_r, 0)
+
+if 'target' in which:
+    # north-star target: moment0/1/2 + spectral_smooth on the 4096x4096x2048 cube.  One GPU holds the whole
+    # 137.4 GB cube (smoothing runs in place); N GPUs hold 1/N of the rows each.
+    nchan, ny, nx = 2048, 4096, 4096
+    y0, y1 = D.row_partition(ny, world)[rank]
+    V = nchan * ny * nx
+    dev = synth_cube(nchan, y1 - y0, nx, y0=y0, ny_total=ny, nx_total=nx, border=102)
+    w = benchmark_wcs(nchan, ny, nx)
+    wl = w.copy(); wl.crpix[1] -= y0
+    c = isfinite_cube(scb.DaskSpectralCube, dev, wl)
+    c = c.with_mask(c > 3.0)
+    S = ny * nx
+    for bits, name in ((1, 'moment0'), (2, 'moment1'), (4, 'moment2'), (7, 'moment0+1+2 in one pass')):
+        ms = timeit(lambda: c._moments_axis0_raw(bits), n=3, warm=1)
+        emit('target', '%s under isfinite & >3 sigma, 4096x4096x2048 (137.4 GB)' % name, V, ms, 4 * V + 8 * S * bin(bits).count('1'))
+    k = scb.Gaussian1DKernel(5 / 2.3548200450309493)
+    c2 = isfinite_cube(scb.DaskSpectralCube, dev, wl)
+    ms = timeit(lambda: c2._run_spectral_smooth(k.array, _lib.F32, out=dev), n=3, warm=1)
+    emit('target', 'spectral_smooth FWHM 5 ch (17 taps), float32, IN PLACE, 4096x4096x2048', V, ms, 8 * V)
+    del dev, c, c2
+    torch.cuda.empty_cache()
 
 if dist is not None:
     dist.destroy_process_group()
