@@ -288,6 +288,27 @@ def run_ours(args):
     torch.cuda.synchronize()
     fused_ms = f0.elapsed_time(f1) / args.steps
 
+    # ---- the other half of the north-star target on the same resident cube: spectral_smooth
+    #      (Gaussian FWHM 5 channels = 17 taps, float32 out, 8 B/voxel) ----
+    smooth_ms = None
+    if not args.no_smooth:
+        iso = scb.DaskSpectralCube(dev, wcs, unit='K')
+        iso._mask = scb.LazyMask(np.isfinite, cube=iso)
+        k17 = scb.Gaussian1DKernel(5 / 2.3548200450309493).array
+        sm_out = torch.empty_like(dev)
+        for _ in range(2):
+            iso._run_spectral_smooth(k17, _lib.F32, out=sm_out)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            iso._run_spectral_smooth(k17, _lib.F32, out=sm_out)
+        s1.record()
+        torch.cuda.synchronize()
+        smooth_ms = s0.elapsed_time(s1) / 5
+        del sm_out, iso
+        torch.cuda.empty_cache()
+
     # ---- end to end: pinned host cube -> upload -> three moments -> host maps ----
     e2e = None
     if not args.no_e2e:
@@ -347,10 +368,20 @@ def run_ours(args):
                         'fused_moment012_one_pass': fused_ms},
         'fused_voxels_per_s': world * voxels / (fused_ms * 1e-3),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'kernel': 'moments_tma_kernel<8,4,INTERVAL,M0|M1|M2> (moment2 call)',
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+                     # ncu --set full capture summarised in profiles/r01_moments_c2_ncu_full.txt
+                     'traffic': 17179959000 + 15093504, 'kernel': 'moments_tma_kernel<8,4,INTERVAL,M0|M1|M2> (moment2 call)',
                      'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': k_ms, 'peak_source': peak_src},
         'e2e': e2e,
     }
+    if smooth_ms is not None:
+        sa = 8 * voxels / (smooth_ms * 1e-3) / 1e9
+        line['spectral_smooth'] = {'ms': smooth_ms, 'voxels_per_s': world * voxels / (smooth_ms * 1e-3),
+                                   'roofline': {'bound': 'hbm', 'achieved': sa, 'peak': peak, 'unit': 'GB/s', 'frac': sa / peak,
+                                                'traffic': 17320210000 + 17214935000,
+                                                'kernel': 'smooth_tma_kernel<8,INTERVAL,f32> (17 taps)',
+                                                'algorithmic_bytes_per_launch': 8 * voxels,
+                                                'ncu': 'profiles/r01_spectral_smooth_ncu_full_v10.txt'}}
     if world == 1 and not args.no_cpu:
         vox, dt, desc = cpu_moments_sample(args.cpu_rows, host_threads())
         line['cpu_baseline'] = {'value': vox / dt, 'unit': 'voxels/s', 'cores': host_threads(), 'kind': 'port',
@@ -370,6 +401,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-smooth', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

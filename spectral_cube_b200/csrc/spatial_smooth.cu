@@ -53,6 +53,9 @@ struct SpatialParams {
     double ty[SP_MAX_TAPS], tx[SP_MAX_TAPS];     // normalised factors, centred in 2H+1, zero padded
     float tyf[SP_MAX_TAPS], txf[SP_MAX_TAPS];
     double tx_scaled[SP_MAX_TAPS];        // tx * 2^896 (the row pass widens float32 by bit placement)
+    uint32_t qy[SP_MAX_TAPS], qx[SP_MAX_TAPS];    // round(t * 2^31): the denominator's exact integer factors (sparse kernel)
+    unsigned long long qall;              // (sum qy) * (sum qx): the denominator with nothing missing
+    double qscale31;                      // qall * 2^(896-31): out = top * qall / present; reciprocal of present >> 31, widened by bit placement
     float lo_closed, hi_closed;          // interval mask as a closed float32 interval
     const uint8_t *passthrough;          // (nchan) 1 = copy the filled plane through; may be NULL
     DevMask mask;
@@ -309,6 +312,313 @@ sep_march_kernel(const __grid_constant__ SpatialParams p) {
     }
 }
 
+// ================================================================================================
+// sep_sparse_kernel -- the separable path for non-negative factors (every Gaussian).
+//
+// Same march as sep_march_kernel for the float64 numerator (row pass -> ring -> column pass, 2(2H+1)
+// FMAs per voxel), but the DENOMINATOR sum_k K[k] ok[..] is no longer convolved: with zero padding
+// counting as valid it equals the full kernel sum everywhere except under a missing input, and missing
+// inputs are rare.  It is therefore kept as an exact integer DEFICIT: the factors are quantised once
+// (qy, qx = round(t 2^31), so every product qy qx is an exact 62-bit integer and sums are order-free),
+// each missing input found while a block is widened is put on a short list, and when an output block
+// is finished every thread adds, for the listed inputs of the 2 HB + 1 blocks around it, qy[ky] qx[kx]
+// to the deficits of its own 8 outputs in registers (zero-padded tables, no branches, no atomics:
+// ~18 instructions per listed input against 2(2H+1) float FMAs per voxel for the convolution).  Blocks
+// with more than SQ_CAP missing inputs (blanked frames, masked regions) switch to the same sum as a
+// separable INTEGER convolution (row deficits in a ring, column gather), which adds exactly the same
+// integers -- results do not depend on which path a block took.  present = qall - deficit == 0 is the exact
+// "nothing valid under the kernel" test; otherwise out = top * qall / present through a float
+// reciprocal (relative error ~1e-7, as before).
+//
+// Other changes: every input is widened to float64 ONCE into a padded shared-memory row (the row pass
+// of sep_march_kernel widened each input five times); rows of the widened block and of the ring are
+// padded by 16 bytes so that the eight threads of an LDS.128/STS.128 phase (eight different rows, same
+// octet) hit eight different bank groups; the centre values for the rare "nothing valid" outputs are
+// re-read from global memory instead of being carried in a third ring.
+// ================================================================================================
+constexpr int SQ_CAP = 8;                // missing inputs per block handled one by one
+constexpr int SQ_QXOFF = SP_W;           // kx = xo - cin + SP_HP + H lies in (-SP_W, SP_TX + 2 SP_HP)
+constexpr int SQ_QXP = SP_W + SP_TX + 2 * SP_HP + 8;
+constexpr int SQ_QYOFF = 32;             // ky = H - dy + ro lies in [H - 2 HB 8 - 7, H + 2 HB 8 + 7]
+constexpr int SQ_QYP = 96;
+constexpr int SQ_WD = SP_W + 2;          // padded row of the widened block (doubles)
+constexpr int SQ_TOP = SP_TX + 2;        // padded ring row (doubles)
+
+// Rare outputs of the sparse kernel, out of line: a plane that is copied through, nothing valid under the
+// kernel (present == 0: the filled input), or almost nothing valid (present < 2^55: exact division).
+__device__ __noinline__ double sparse_rare_output(const SpatialParams &p, double top, unsigned long long present, bool pass,
+                                                  int64_t c, int64_t y, int64_t x) {
+    if (present == 0ull || pass) {
+        float cv = __ldg(p.in + c * p.stride_c + y * p.stride_y + x);
+        if (!mask_include_rt(p.mask, cv, c, y, x)) cv = p.fill;
+        return (double)cv;
+    }
+    return top * ((double)p.qall / (double)present);
+}
+
+template <int NB>
+struct SparseSmem {
+    double top[NB * SP_R][SQ_TOP];
+    double wd[SP_R][SQ_WD];
+    uint32_t dxi[NB * SP_R][SP_TX];
+    uint32_t qxp[SQ_QXP];                         // qx[k] at index k + SQ_QXOFF, zero elsewhere
+    uint32_t qyp[SQ_QYP];                         // qy[k] at index k + SQ_QYOFF, zero elsewhere
+    float raw[SP_RS][SP_R][SP_W];
+    uint16_t list[NB][SQ_CAP];
+    int count[NB];
+    uint8_t bad[SP_R][SP_W];
+    uint64_t full[SP_RS];
+    uint64_t empty[SP_RS];
+};
+
+template <int H, int OUT64>
+__global__ void __launch_bounds__(SP_THREADS, 2)
+sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
+    constexpr int NT = 2 * H + 1;
+    constexpr int HB = (H + SP_R - 1) / SP_R;            // halo in blocks
+    constexpr int NB = 2 * HB + 2;                       // ring of row-passed blocks
+    constexpr int NIN_X = SP_R + 2 * SP_HP;              // 40 inputs per row-pass thread (aligned superset)
+    constexpr int NIN_Y = SP_R + 2 * H;
+    static_assert(H <= SP_HP, "horizontal halo too small");
+    static_assert(SP_R * SP_W == 10 * SP_TX, "the widening pass covers the block in 10 sweeps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SparseSmem<NB> &sm = *reinterpret_cast<SparseSmem<NB> *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    // blockIdx.x = ((c * chunks) + chunk) * strips + strip
+    int64_t bid = blockIdx.x;
+    const int strip = (int)(bid % p.strips_per_row); bid /= p.strips_per_row;
+    const int chunk = (int)(bid % p.chunks);
+    const int64_t c = bid / p.chunks;
+    const int64_t x0 = (int64_t)strip * SP_TX;
+    const int64_t ya = (int64_t)chunk * p.rows_per_cta;
+    const int64_t yb = min(p.ny, ya + p.rows_per_cta);
+    const int nout_blk = (int)((yb - ya + SP_R - 1) / SP_R);
+    const int nblk = nout_blk + 2 * HB;                  // blocks to row-pass
+    const int64_t y_first = ya - (int64_t)HB * SP_R;     // first row of block 0
+
+    const int64_t xl = max((int64_t)0, x0 - SP_HP), xr = min(p.nx, x0 + SP_TX + SP_HP);
+    const int col_off = (int)(xl - (x0 - SP_HP));
+    const uint32_t row_bytes = (uint32_t)(xr - xl) * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < SP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SP_TX / 32); }
+        mbar_fence_init();
+    }
+    if (tid < NB) sm.count[tid] = 0;
+    for (int i = tid; i < SQ_QXP; i += SP_THREADS) { const int k = i - SQ_QXOFF; sm.qxp[i] = (k >= 0 && k < NT) ? p.qx[k] : 0u; }
+    for (int i = tid; i < SQ_QYP; i += SP_THREADS) { const int k = i - SQ_QYOFF; sm.qyp[i] = (k >= 0 && k < NT) ? p.qy[k] : 0u; }
+    __syncthreads();
+
+    if (warp == SP_TX / 32) {
+        // ---------------- producer warp: raw rows of block b -> raw[b % RS] ----------------
+        const uint64_t pol = l2_evict_first_policy();
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b % SP_RS;
+            if (b >= SP_RS) mbar_wait(&sm.empty[s], ((b / SP_RS) - 1) & 1);
+            const float *src = nullptr;
+            if (lane < SP_R) {
+                const int64_t y = y_first + (int64_t)b * SP_R + lane;
+                if (y >= 0 && y < p.ny) src = p.in + c * p.stride_c + y * p.stride_y + xl;
+                else if (y < 0 && p.halo_top && y >= -p.halo_rows)
+                    src = p.halo_top + (c * p.halo_rows + (p.halo_rows + y)) * p.nx + xl;
+                else if (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows)
+                    src = p.halo_bot + (c * p.halo_rows + (y - p.ny)) * p.nx + xl;
+            }
+            const unsigned have = __ballot_sync(0xffffffffu, src != nullptr);
+            if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)__popc(have) * row_bytes);
+            __syncwarp();
+            if (src) tma_load_1d(&sm.raw[s][lane][col_off], src, row_bytes, &sm.full[s], pol);
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const bool pass = p.passthrough && p.passthrough[c];
+    const bool strip_clipped = xl != x0 - SP_HP || xr != x0 + SP_TX + SP_HP;
+    const bool mask_by_sweep = p.mask.mode == MODE_GENERIC || (p.mask.mode == MODE_INTERVAL && p.fill == p.fill);
+    const int rrow = tid & 7;             // row-pass mapping: row of the block (fastest: bank spread) ...
+    const int roct = tid >> 3;            // ... and octet of columns
+
+    for (int b = 0; b < nblk; ++b) {
+        const int s = b % SP_RS;
+        const int rb = b % NB;
+        const int64_t yblk = y_first + (int64_t)b * SP_R;
+        mbar_wait(&sm.full[s], (b / SP_RS) & 1);
+
+        // (1) Only where needed (uniform per block): zero what the copy did not cover and apply masks that
+        //     the validity test below cannot express.
+        const bool rows_inside = yblk >= (p.halo_top ? -(int64_t)p.halo_rows : 0) &&
+                                 yblk + SP_R <= p.ny + (p.halo_bot ? (int64_t)p.halo_rows : 0);
+        const bool sweep = strip_clipped || !rows_inside || mask_by_sweep;
+        float lo_c = -INFINITY, hi_c = INFINITY;                     // closed validity interval
+        if (sweep) {
+#pragma unroll 1
+            for (int r = 0; r < SP_R; ++r) {
+                const int64_t y = yblk + r;                          // uniform
+                const bool own = y >= 0 && y < p.ny;
+                const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
+                const bool need_mask = own && p.mask.mode != MODE_NONE;
+                for (int col = tid; col < SP_W; col += SP_TX) {
+                    const int64_t x = x0 - SP_HP + col;
+                    float v = 0.0f;                                  // outside the image: a valid zero
+                    if (x >= xl && x < xr && (own || halo)) {
+                        v = sm.raw[s][r][col];
+                        if (need_mask && !mask_include_rt(p.mask, v, c, y, x)) v = p.fill;
+                    }
+                    sm.raw[s][r][col] = v;
+                }
+            }
+            compute_bar();
+        } else if (p.mask.mode == MODE_INTERVAL) {
+            lo_c = p.lo_closed; hi_c = p.hi_closed;                  // excluded == NaN-filled == "missing"
+        }
+
+        // (2) widen every input once; list the missing ones.  Thread tid takes column tid of the 8 rows and
+        //     two of the 32 x 8 samples of the right-hand halo (all indices but tid are compile-time).
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int row = i < 8 ? i : (warp + (i - 8) * 4);
+            const int col = i < 8 ? tid : SP_TX + lane;
+            const float v = sm.raw[s][row][col];
+            const bool ok = (v >= lo_c) & (v <= hi_c);               // false for NaN
+            sm.wd[row][col] = place_scaled_sp(ok ? v : 0.0f);
+            sm.bad[row][col] = ok ? 0 : 1;
+            if (!ok) {
+                const int idx = atomicAdd(&sm.count[rb], 1);
+                if (idx < SQ_CAP) sm.list[rb][idx] = (uint16_t)((row << 8) | col);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);                    // the raw rows are not read again
+        compute_bar();
+        // next block's counter: its old block was last read in step b - 1, which every warp has left by now
+        if (tid == 0) sm.count[(b + 1) % NB] = 0;
+
+        // (3) row pass: 8 adjacent outputs of row `rrow` from 40 widened inputs
+        {
+            double w[NIN_X];
+#pragma unroll
+            for (int q = 0; q < NIN_X / 2; ++q) {
+                const double2 d2 = *reinterpret_cast<const double2 *>(&sm.wd[rrow][roct * 8 + q * 2]);
+                w[q * 2] = d2.x; w[q * 2 + 1] = d2.y;
+            }
+            const int slot = rb * SP_R + rrow;
+            double top[SP_R];
+#pragma unroll
+            for (int j = 0; j < SP_R; ++j) top[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {                           // tap-outer: each tap is fetched once
+                const double t = p.tx_scaled[k];
+#pragma unroll
+                for (int j = 0; j < SP_R; ++j) top[j] = fma(t, w[j + SP_HP + H - k], top[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < SP_R; j += 2)
+                *reinterpret_cast<double2 *>(&sm.top[slot][roct * 8 + j]) = make_double2(top[j], top[j + 1]);
+            if (sm.count[rb] > SQ_CAP) {
+                // crowded block: row deficits as an integer convolution of the missing flags
+                uint32_t dx[SP_R];
+#pragma unroll
+                for (int j = 0; j < SP_R; ++j) dx[j] = 0u;
+#pragma unroll 1
+                for (int k = 0; k < NT; ++k) {
+                    const uint32_t q = p.qx[k];
+#pragma unroll
+                    for (int j = 0; j < SP_R; ++j) dx[j] += q * (uint32_t)sm.bad[rrow][roct * 8 + j + SP_HP + H - k];
+                }
+#pragma unroll
+                for (int j = 0; j < SP_R; ++j) sm.dxi[slot][roct * 8 + j] = dx[j];
+            }
+        }
+        compute_bar();
+
+        // (4) output block j = b - 2 HB (its rows are block b - HB of the march)
+        if (b >= 2 * HB) {
+            const int jb = b - HB;
+            const int64_t yout = y_first + (int64_t)jb * SP_R;
+            // ---- deficit of this thread's 8 outputs (column tid) from the 2 HB + 1 input blocks around them:
+            //      exact integers in registers, no atomics ----
+            unsigned long long def[SP_R];
+#pragma unroll
+            for (int ro = 0; ro < SP_R; ++ro) def[ro] = 0ull;
+#pragma unroll
+            for (int t = 0; t < 2 * HB + 1; ++t) {
+                const int st = (b - 2 * HB + t) % NB;
+                const int cnt = sm.count[st];                        // uniform
+                if (cnt == 0) continue;
+                if (cnt <= SQ_CAP) {
+                    // few: one listed input at a time; tables padded with zeros make every product valid
+#pragma unroll 1
+                    for (int n = 0; n < cnt; ++n) {
+                        const int ent = sm.list[st][n];              // uniform
+                        const int r_in = ent >> 8, cin = ent & 255;
+                        const uint32_t qxv = sm.qxp[tid - cin + SP_HP + H + SQ_QXOFF];          // qx[kx], kx = xo - xi + H
+                        const uint32_t *qyr = &sm.qyp[H - ((t - HB) * SP_R + r_in) + SQ_QYOFF];   // qy[ky], ky = H - (yi - yo)
+#pragma unroll
+                        for (int ro = 0; ro < SP_R; ++ro) def[ro] += (unsigned long long)qyr[ro] * qxv;
+                    }
+                } else {
+                    // crowded: gather this block's row deficits down the column
+#pragma unroll
+                    for (int r_in = 0; r_in < SP_R; ++r_in) {
+                        const unsigned long long d = sm.dxi[st * SP_R + r_in][tid];
+#pragma unroll
+                        for (int ro = 0; ro < SP_R; ++ro) {
+                            const int ky = H - ((t - HB) * SP_R + r_in - ro);      // compile time
+                            if (ky >= 0 && ky <= 2 * H) def[ro] += d * (unsigned long long)p.qy[ky];
+                        }
+                    }
+                }
+            }
+
+            // ---- column pass ----
+            double w[NIN_Y];
+            int slot_of[2 * HB + 1];
+            {
+                int sl = (b - 2 * HB) % NB;
+#pragma unroll
+                for (int t = 0; t < 2 * HB + 1; ++t) { slot_of[t] = sl * SP_R; sl = (sl + 1 == NB) ? 0 : sl + 1; }
+            }
+#pragma unroll
+            for (int i = 0; i < NIN_Y; ++i) {
+                const int rel = HB * SP_R - H + i;                   // compile-time: row relative to block b - 2HB
+                w[i] = sm.top[slot_of[rel / SP_R] + (rel % SP_R)][tid];
+            }
+            const int64_t x = x0 + tid;
+            double top[SP_R];
+#pragma unroll
+            for (int r = 0; r < SP_R; ++r) top[r] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const double t = p.ty[k];
+#pragma unroll
+                for (int r = 0; r < SP_R; ++r) top[r] = fma(t, w[r + 2 * H - k], top[r]);
+            }
+            char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
+            const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
+            // out = top * qall / present.  Common path without branches: float reciprocal of the top 32 bits of
+            // `present` (exact to 2^-24 when present >= 2^55), widened by bit placement; d == 0 keeps `top` as it
+            // is.  Rare, under one vote: a plane copied through, nothing valid (present == 0: the filled input)
+            // or almost nothing valid (present < 2^55: exact division).
+#pragma unroll
+            for (int r = 0; r < SP_R; ++r) {
+                const unsigned long long present = p.qall - def[r];
+                const uint32_t hi = (uint32_t)(present >> 31);
+                const double rcp = place_scaled_sp(__frcp_rn((float)hi)) * p.qscale31;
+                double res = def[r] != 0ull ? top[r] * rcp : top[r];
+                const bool live = yout + r < yb && x < p.nx;
+                if ((hi < (1u << 24) || pass) && live) res = sparse_rare_output(p, top[r], present, pass, c, yout + r, x);
+                if (live) {
+                    if (OUT64) *reinterpret_cast<double *>(op + r * ostep) = res;
+                    else       *reinterpret_cast<float *>(op + r * ostep) = (float)res;
+                }
+            }
+        }
+    }
+}
+
 // ---- direct 2-D kernel: any odd x odd taps ------------------------------------------------------------
 struct DirectParams {
     SpatialParams sp;
@@ -415,6 +725,34 @@ static cudaError_t launch_sep_one(const SpatialParams &p, unsigned grid, cudaStr
     return cudaGetLastError();
 }
 
+template <int H, int OUT64>
+static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    constexpr int HB = (H + SP_R - 1) / SP_R;
+    constexpr int NB = 2 * HB + 2;
+    auto kern = sep_sparse_kernel<H, OUT64>;
+    const size_t smem = sizeof(SparseSmem<NB>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, SP_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int OUT64>
+static cudaError_t launch_sparse_h(const SpatialParams &p, int h, unsigned grid, cudaStream_t s) {
+    if (h <= 2)  return launch_sparse_one<2, OUT64>(p, grid, s);
+    if (h <= 4)  return launch_sparse_one<4, OUT64>(p, grid, s);
+    if (h <= 6)  return launch_sparse_one<6, OUT64>(p, grid, s);
+    if (h <= 8)  return launch_sparse_one<8, OUT64>(p, grid, s);
+    if (h <= 10) return launch_sparse_one<10, OUT64>(p, grid, s);
+    if (h <= 12) return launch_sparse_one<12, OUT64>(p, grid, s);
+    if (h <= 14) return launch_sparse_one<14, OUT64>(p, grid, s);
+    return launch_sparse_one<16, OUT64>(p, grid, s);
+}
+
 template <int OUT64>
 static cudaError_t launch_sep_h(const SpatialParams &p, int h, unsigned grid, cudaStream_t s) {
     if (h <= 2)  return launch_sep_one<2, OUT64>(p, grid, s);
@@ -500,9 +838,25 @@ extern "C" int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
         p.chunks = (int)cdiv(ny, p.rows_per_cta);
         const int64_t grid = base * p.chunks;
         SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
+        // integer factors of the denominator (sparse kernel): needs factors in [0, 1]
+        bool nonneg = true;
+        unsigned long long qsy = 0, qsx = 0;
+        for (int k = 0; k < SP_MAX_TAPS; ++k) {
+            nonneg = nonneg && p.ty[k] >= 0.0 && p.tx[k] >= 0.0 && p.ty[k] <= 1.0 && p.tx[k] <= 1.0;
+            p.qy[k] = (uint32_t)llrint(fmin(fmax(p.ty[k], 0.0), 1.0) * 2147483648.0);
+            p.qx[k] = (uint32_t)llrint(fmin(fmax(p.tx[k], 0.0), 1.0) * 2147483648.0);
+            qsy += p.qy[k]; qsx += p.qx[k];
+        }
+        nonneg = nonneg && qsy < (1ull << 32) && qsx < (1ull << 32) && qsy > 0 && qsx > 0;
+        p.qall = qsy * qsx;
+        p.qscale31 = ldexp((double)p.qall, 896 - 31);
         LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
-        cudaError_t e = out_dtype == SC_F64 ? launch_sep_h<1>(p, H, (unsigned)grid, s) : launch_sep_h<0>(p, H, (unsigned)grid, s);
-        if (e != cudaSuccess) return cuda_fail(e, "sep_march_kernel launch");
+        cudaError_t e;
+        if (nonneg && choice != 3)
+            e = out_dtype == SC_F64 ? launch_sparse_h<1>(p, H, (unsigned)grid, s) : launch_sparse_h<0>(p, H, (unsigned)grid, s);
+        else
+            e = out_dtype == SC_F64 ? launch_sep_h<1>(p, H, (unsigned)grid, s) : launch_sep_h<0>(p, H, (unsigned)grid, s);
+        if (e != cudaSuccess) return cuda_fail(e, "separable spatial kernel launch");
         return SC_OK;
     }
     // fall back to the direct kernel on the outer product
