@@ -371,16 +371,28 @@ struct SparseSmem {
     uint64_t empty[SP_RS];
 };
 
+constexpr int SQ_CT = 256;               // compute threads: 8 warps share one 8 x 128 block
+constexpr int SQ_THREADS = SQ_CT + 32;   // + the producer warp
+
+__device__ __forceinline__ void sparse_bar() {           // barrier among the SQ_CT compute threads only
+    asm volatile("bar.sync 1, %0;" :: "n"(SQ_CT) : "memory");
+}
+
+// Work split (256 compute threads per 8 x 128 block, half the serial work per warp of a 128-thread
+// CTA -- the kernel is bound by the latency of its phases, not by issue slots):
+//   widening   thread -> column tid & 127 of rows 2i + (tid >> 7), plus one sample of the right-hand halo;
+//   row pass   thread -> row tid & 7 (fastest: eight rows = eight bank groups), columns 4 (tid >> 3) .. + 3;
+//   column pass thread -> column tid & 127, output rows 4 (tid >> 7) .. + 3.
 template <int H, int OUT64>
-__global__ void __launch_bounds__(SP_THREADS, 2)
+__global__ void __launch_bounds__(SQ_THREADS, 2)
 sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
     constexpr int NT = 2 * H + 1;
     constexpr int HB = (H + SP_R - 1) / SP_R;            // halo in blocks
     constexpr int NB = 2 * HB + 2;                       // ring of row-passed blocks
-    constexpr int NIN_X = SP_R + 2 * SP_HP;              // 40 inputs per row-pass thread (aligned superset)
-    constexpr int NIN_Y = SP_R + 2 * H;
+    constexpr int RQ = 4;                                // outputs per thread in both passes
+    constexpr int NIN_X = RQ + 2 * SP_HP;                // 36 inputs per row-pass thread (aligned superset)
+    constexpr int NIN_Y = RQ + 2 * H;
     static_assert(H <= SP_HP, "horizontal halo too small");
-    static_assert(SP_R * SP_W == 10 * SP_TX, "the widening pass covers the block in 10 sweeps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SparseSmem<NB> &sm = *reinterpret_cast<SparseSmem<NB> *>(smem_raw);
 
@@ -403,15 +415,15 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
     const uint32_t row_bytes = (uint32_t)(xr - xl) * 4u;
 
     if (tid == 0) {
-        for (int s = 0; s < SP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SP_TX / 32); }
+        for (int s = 0; s < SP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SQ_CT / 32); }
         mbar_fence_init();
     }
     if (tid < NB) sm.count[tid] = 0;
-    for (int i = tid; i < SQ_QXP; i += SP_THREADS) { const int k = i - SQ_QXOFF; sm.qxp[i] = (k >= 0 && k < NT) ? p.qx[k] : 0u; }
-    for (int i = tid; i < SQ_QYP; i += SP_THREADS) { const int k = i - SQ_QYOFF; sm.qyp[i] = (k >= 0 && k < NT) ? p.qy[k] : 0u; }
+    for (int i = tid; i < SQ_QXP; i += SQ_THREADS) { const int k = i - SQ_QXOFF; sm.qxp[i] = (k >= 0 && k < NT) ? p.qx[k] : 0u; }
+    for (int i = tid; i < SQ_QYP; i += SQ_THREADS) { const int k = i - SQ_QYOFF; sm.qyp[i] = (k >= 0 && k < NT) ? p.qy[k] : 0u; }
     __syncthreads();
 
-    if (warp == SP_TX / 32) {
+    if (warp == SQ_CT / 32) {
         // ---------------- producer warp: raw rows of block b -> raw[b % RS] ----------------
         const uint64_t pol = l2_evict_first_policy();
         for (int b = 0; b < nblk; ++b) {
@@ -438,8 +450,10 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
     const bool pass = p.passthrough && p.passthrough[c];
     const bool strip_clipped = xl != x0 - SP_HP || xr != x0 + SP_TX + SP_HP;
     const bool mask_by_sweep = p.mask.mode == MODE_GENERIC || (p.mask.mode == MODE_INTERVAL && p.fill == p.fill);
-    const int rrow = tid & 7;             // row-pass mapping: row of the block (fastest: bank spread) ...
-    const int roct = tid >> 3;            // ... and octet of columns
+    const int rrow = tid & 7;             // row pass: row of the block ...
+    const int rq = tid >> 3;              // ... and quad of columns
+    const int ccol = tid & (SP_TX - 1);   // column pass: column ...
+    const int chalf = tid >> 7;           // ... and half of the output block (rows 4 chalf .. + 3)
 
     for (int b = 0; b < nblk; ++b) {
         const int s = b % SP_RS;
@@ -460,7 +474,7 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
                 const bool own = y >= 0 && y < p.ny;
                 const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
                 const bool need_mask = own && p.mask.mode != MODE_NONE;
-                for (int col = tid; col < SP_W; col += SP_TX) {
+                for (int col = tid; col < SP_W; col += SQ_CT) {
                     const int64_t x = x0 - SP_HP + col;
                     float v = 0.0f;                                  // outside the image: a valid zero
                     if (x >= xl && x < xr && (own || halo)) {
@@ -470,17 +484,16 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
                     sm.raw[s][r][col] = v;
                 }
             }
-            compute_bar();
+            sparse_bar();
         } else if (p.mask.mode == MODE_INTERVAL) {
             lo_c = p.lo_closed; hi_c = p.hi_closed;                  // excluded == NaN-filled == "missing"
         }
 
-        // (2) widen every input once; list the missing ones.  Thread tid takes column tid of the 8 rows and
-        //     two of the 32 x 8 samples of the right-hand halo (all indices but tid are compile-time).
+        // (2) widen every input once; list the missing ones (all indices but tid are compile-time)
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const int row = i < 8 ? i : (warp + (i - 8) * 4);
-            const int col = i < 8 ? tid : SP_TX + lane;
+        for (int i = 0; i < 5; ++i) {
+            const int row = i < 4 ? 2 * i + chalf : warp;
+            const int col = i < 4 ? ccol : SP_TX + lane;
             const float v = sm.raw[s][row][col];
             const bool ok = (v >= lo_c) & (v <= hi_c);               // false for NaN
             sm.wd[row][col] = place_scaled_sp(ok ? v : 0.0f);
@@ -492,57 +505,57 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);                    // the raw rows are not read again
-        compute_bar();
+        sparse_bar();
         // next block's counter: its old block was last read in step b - 1, which every warp has left by now
         if (tid == 0) sm.count[(b + 1) % NB] = 0;
 
-        // (3) row pass: 8 adjacent outputs of row `rrow` from 40 widened inputs
+        // (3) row pass: 4 adjacent outputs of row `rrow` from 36 widened inputs
         {
             double w[NIN_X];
 #pragma unroll
             for (int q = 0; q < NIN_X / 2; ++q) {
-                const double2 d2 = *reinterpret_cast<const double2 *>(&sm.wd[rrow][roct * 8 + q * 2]);
+                const double2 d2 = *reinterpret_cast<const double2 *>(&sm.wd[rrow][rq * RQ + q * 2]);
                 w[q * 2] = d2.x; w[q * 2 + 1] = d2.y;
             }
             const int slot = rb * SP_R + rrow;
-            double top[SP_R];
+            double top[RQ];
 #pragma unroll
-            for (int j = 0; j < SP_R; ++j) top[j] = 0.0;
+            for (int j = 0; j < RQ; ++j) top[j] = 0.0;
 #pragma unroll
             for (int k = 0; k < NT; ++k) {                           // tap-outer: each tap is fetched once
                 const double t = p.tx_scaled[k];
 #pragma unroll
-                for (int j = 0; j < SP_R; ++j) top[j] = fma(t, w[j + SP_HP + H - k], top[j]);
+                for (int j = 0; j < RQ; ++j) top[j] = fma(t, w[j + SP_HP + H - k], top[j]);
             }
 #pragma unroll
-            for (int j = 0; j < SP_R; j += 2)
-                *reinterpret_cast<double2 *>(&sm.top[slot][roct * 8 + j]) = make_double2(top[j], top[j + 1]);
+            for (int j = 0; j < RQ; j += 2)
+                *reinterpret_cast<double2 *>(&sm.top[slot][rq * RQ + j]) = make_double2(top[j], top[j + 1]);
             if (sm.count[rb] > SQ_CAP) {
                 // crowded block: row deficits as an integer convolution of the missing flags
-                uint32_t dx[SP_R];
+                uint32_t dx[RQ];
 #pragma unroll
-                for (int j = 0; j < SP_R; ++j) dx[j] = 0u;
+                for (int j = 0; j < RQ; ++j) dx[j] = 0u;
 #pragma unroll 1
                 for (int k = 0; k < NT; ++k) {
                     const uint32_t q = p.qx[k];
 #pragma unroll
-                    for (int j = 0; j < SP_R; ++j) dx[j] += q * (uint32_t)sm.bad[rrow][roct * 8 + j + SP_HP + H - k];
+                    for (int j = 0; j < RQ; ++j) dx[j] += q * (uint32_t)sm.bad[rrow][rq * RQ + j + SP_HP + H - k];
                 }
 #pragma unroll
-                for (int j = 0; j < SP_R; ++j) sm.dxi[slot][roct * 8 + j] = dx[j];
+                for (int j = 0; j < RQ; ++j) sm.dxi[slot][rq * RQ + j] = dx[j];
             }
         }
-        compute_bar();
+        sparse_bar();
 
         // (4) output block j = b - 2 HB (its rows are block b - HB of the march)
         if (b >= 2 * HB) {
             const int jb = b - HB;
-            const int64_t yout = y_first + (int64_t)jb * SP_R;
-            // ---- deficit of this thread's 8 outputs (column tid) from the 2 HB + 1 input blocks around them:
+            const int64_t yout = y_first + (int64_t)jb * SP_R + chalf * RQ;      // this thread's first output row
+            // ---- deficit of this thread's 4 outputs from the 2 HB + 1 input blocks around them:
             //      exact integers in registers, no atomics ----
-            unsigned long long def[SP_R];
+            unsigned long long def[RQ];
 #pragma unroll
-            for (int ro = 0; ro < SP_R; ++ro) def[ro] = 0ull;
+            for (int ro = 0; ro < RQ; ++ro) def[ro] = 0ull;
 #pragma unroll
             for (int t = 0; t < 2 * HB + 1; ++t) {
                 const int st = (b - 2 * HB + t) % NB;
@@ -554,56 +567,52 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
                     for (int n = 0; n < cnt; ++n) {
                         const int ent = sm.list[st][n];              // uniform
                         const int r_in = ent >> 8, cin = ent & 255;
-                        const uint32_t qxv = sm.qxp[tid - cin + SP_HP + H + SQ_QXOFF];          // qx[kx], kx = xo - xi + H
-                        const uint32_t *qyr = &sm.qyp[H - ((t - HB) * SP_R + r_in) + SQ_QYOFF];   // qy[ky], ky = H - (yi - yo)
+                        const uint32_t qxv = sm.qxp[ccol - cin + SP_HP + H + SQ_QXOFF];                          // qx[kx], kx = xo - xi + H
+                        const uint32_t *qyr = &sm.qyp[H - ((t - HB) * SP_R + r_in) + chalf * RQ + SQ_QYOFF];     // qy[ky], ky = H - (yi - yo)
 #pragma unroll
-                        for (int ro = 0; ro < SP_R; ++ro) def[ro] += (unsigned long long)qyr[ro] * qxv;
+                        for (int ro = 0; ro < RQ; ++ro) def[ro] += (unsigned long long)qyr[ro] * qxv;
                     }
                 } else {
                     // crowded: gather this block's row deficits down the column
 #pragma unroll
                     for (int r_in = 0; r_in < SP_R; ++r_in) {
-                        const unsigned long long d = sm.dxi[st * SP_R + r_in][tid];
+                        const unsigned long long d = sm.dxi[st * SP_R + r_in][ccol];
+                        const uint32_t *qyr = &sm.qyp[H - ((t - HB) * SP_R + r_in) + chalf * RQ + SQ_QYOFF];
 #pragma unroll
-                        for (int ro = 0; ro < SP_R; ++ro) {
-                            const int ky = H - ((t - HB) * SP_R + r_in - ro);      // compile time
-                            if (ky >= 0 && ky <= 2 * H) def[ro] += d * (unsigned long long)p.qy[ky];
-                        }
+                        for (int ro = 0; ro < RQ; ++ro) def[ro] += d * (unsigned long long)qyr[ro];
                     }
                 }
             }
 
-            // ---- column pass ----
+            // ---- column pass: 4 outputs from 4 + 2H ring rows starting at ring row r0 ----
             double w[NIN_Y];
-            int slot_of[2 * HB + 1];
             {
-                int sl = (b - 2 * HB) % NB;
+                int rr = ((b - 2 * HB) % NB) * SP_R + HB * SP_R - H + chalf * RQ;     // ring row of w[0]
+                if (rr >= NB * SP_R) rr -= NB * SP_R;
 #pragma unroll
-                for (int t = 0; t < 2 * HB + 1; ++t) { slot_of[t] = sl * SP_R; sl = (sl + 1 == NB) ? 0 : sl + 1; }
+                for (int i = 0; i < NIN_Y; ++i) {
+                    w[i] = sm.top[rr][ccol];
+                    rr = (rr + 1 == NB * SP_R) ? 0 : rr + 1;
+                }
             }
+            const int64_t x = x0 + ccol;
+            double top[RQ];
 #pragma unroll
-            for (int i = 0; i < NIN_Y; ++i) {
-                const int rel = HB * SP_R - H + i;                   // compile-time: row relative to block b - 2HB
-                w[i] = sm.top[slot_of[rel / SP_R] + (rel % SP_R)][tid];
-            }
-            const int64_t x = x0 + tid;
-            double top[SP_R];
-#pragma unroll
-            for (int r = 0; r < SP_R; ++r) top[r] = 0.0;
+            for (int r = 0; r < RQ; ++r) top[r] = 0.0;
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
                 const double t = p.ty[k];
 #pragma unroll
-                for (int r = 0; r < SP_R; ++r) top[r] = fma(t, w[r + 2 * H - k], top[r]);
+                for (int r = 0; r < RQ; ++r) top[r] = fma(t, w[r + 2 * H - k], top[r]);
             }
             char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
             const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
             // out = top * qall / present.  Common path without branches: float reciprocal of the top 32 bits of
-            // `present` (exact to 2^-24 when present >= 2^55), widened by bit placement; d == 0 keeps `top` as it
-            // is.  Rare, under one vote: a plane copied through, nothing valid (present == 0: the filled input)
-            // or almost nothing valid (present < 2^55: exact division).
+            // `present` (exact to 2^-24 when present >= 2^55), widened by bit placement; a zero deficit keeps
+            // `top` as it is.  Rare, out of line: a plane copied through, nothing valid (present == 0: the
+            // filled input) or almost nothing valid (present < 2^55: exact division).
 #pragma unroll
-            for (int r = 0; r < SP_R; ++r) {
+            for (int r = 0; r < RQ; ++r) {
                 const unsigned long long present = p.qall - def[r];
                 const uint32_t hi = (uint32_t)(present >> 31);
                 const double rcp = place_scaled_sp(__frcp_rn((float)hi)) * p.qscale31;
@@ -737,7 +746,7 @@ static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cuda
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, SP_THREADS, smem, s>>>(p);
+    kern<<<grid, SQ_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
