@@ -283,6 +283,18 @@ int sc_reproject(const float *in, void *out, int out_dtype, uint8_t *footprint,
                  const sc_mask_desc *mask, double fill,
                  const double *yin, const double *xin, int order, void *stream);
 
+/* The same in one pass with the by-products the caller of `reproject_interp` derives afterwards
+ * (spectral_cube.py:2733-2746): `out_f32` (may be NULL) receives the result rounded to float32
+ * next to the `out` of dtype `out_dtype` (the new cube's float32 working copy), and
+ * `*any_valid` (device int32, may be NULL; zeroed by the call) is set to 1 when at least one output
+ * voxel is not NaN -- the "All values in reprojected cube are nan" test without another pass. */
+int sc_reproject_ex(const float *in, void *out, int out_dtype, float *out_f32, uint8_t *footprint, int *any_valid,
+                    int64_t nchan, int64_t ny_in, int64_t nx_in,
+                    int64_t stride_c, int64_t stride_y,
+                    int64_t ny_out, int64_t nx_out,
+                    const sc_mask_desc *mask, double fill,
+                    const double *yin, const double *xin, int order, void *stream);
+
 /* Celestial pixel->pixel map for two TAN/SIN WCSs (the part of `reproject_interp` that
  * runs through astropy.wcs; FITS WCS papers I/II).  wcs_* = 12 doubles:
  * crpix1, crpix2, crval1, crval2, cd11, cd12, cd21, cd22, lonpole, proj(0 TAN,1 SIN), 0, 0.

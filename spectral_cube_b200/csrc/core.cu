@@ -43,6 +43,11 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint
 
 int make_cube_tensor_map(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
                          int64_t stride_c, int64_t stride_y, int box_x, int box_c) {
+    return make_cube_tensor_map3(out, base, nchan, ny, nx, stride_c, stride_y, box_x, 1, box_c);
+}
+
+int make_cube_tensor_map3(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
+                          int64_t stride_c, int64_t stride_y, int box_x, int box_y, int box_c) {
     static std::atomic<TensorMapEncodeFn> cached{nullptr};
     TensorMapEncodeFn fn = cached.load(std::memory_order_acquire);
     if (!fn) {
@@ -59,7 +64,7 @@ int make_cube_tensor_map(CUtensorMap *out, const float *base, int64_t nchan, int
     // a one-row cube still needs a non-zero plane stride for the descriptor
     const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nchan};
     const cuuint64_t strides[2] = {(cuuint64_t)stride_y * 4u, (cuuint64_t)stride_c * 4u};
-    const cuuint32_t box[3] = {(cuuint32_t)box_x, 1u, (cuuint32_t)box_c};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)box_c};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -74,6 +74,9 @@ __device__ __forceinline__ void tma_load_box3d(void *smem_dst, const CUtensorMap
 // Needs base % 16 == 0, stride_y % 4 == 0, stride_c % 4 == 0, box_x % 4 == 0, box_x, box_c <= 256.
 int make_cube_tensor_map(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
                          int64_t stride_c, int64_t stride_y, int box_x, int box_c);
+// the same with a box {box_x, box_y, box_c}
+int make_cube_tensor_map3(CUtensorMap *out, const float *base, int64_t nchan, int64_t ny, int64_t nx,
+                          int64_t stride_c, int64_t stride_y, int box_x, int box_y, int box_c);
 
 // shared -> global bulk store (bulk_group completion)
 __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {

@@ -475,6 +475,8 @@ class BaseSpectralCube(object):
         return yin, xin
 
     def _run_reproject(self, yin, xin, order, filled=True, out_dtype=None):
+        """One pass: the float64 result `reproject_interp` returns, its float32 working copy, the
+        footprint and the "anything valid at all" flag (spectral_cube.py:2726-2746)."""
         torch = _torch()
         lib = _lib.load()
         src = self._data
@@ -483,12 +485,15 @@ class BaseSpectralCube(object):
         out_dtype = _lib.F64 if out_dtype is None else out_dtype
         out = torch.empty((nchan, ny_out, nx_out), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
                           device=src.device)
+        out32 = torch.empty((nchan, ny_out, nx_out), dtype=torch.float32, device=src.device) if out_dtype == _lib.F64 else None
         foot = torch.empty((nchan, ny_out, nx_out), dtype=torch.uint8, device=src.device)
+        flag = torch.empty((1,), dtype=torch.int32, device=src.device)
         desc, keep = self._mask_desc() if filled else lower_mask(None, src)
-        _lib.check(lib.sc_reproject(src.data_ptr(), out.data_ptr(), out_dtype, foot.data_ptr(), nchan, ny, nx,
-                                    src.stride(0), src.stride(1), ny_out, nx_out, desc, float(self._fill_value),
-                                    yin.data_ptr(), xin.data_ptr(), order, _stream()))
-        return out, foot
+        _lib.check(lib.sc_reproject_ex(src.data_ptr(), out.data_ptr(), out_dtype,
+                                       out32.data_ptr() if out32 is not None else None, foot.data_ptr(), flag.data_ptr(),
+                                       nchan, ny, nx, src.stride(0), src.stride(1), ny_out, nx_out, desc,
+                                       float(self._fill_value), yin.data_ptr(), xin.data_ptr(), order, _stream()))
+        return out, (out32 if out32 is not None else out), foot, flag
 
     def reproject(self, header, order='bilinear', use_memmap=False, filled=True, **kwargs):
         """Spatially reproject the cube into a new header (a FITS-header-like mapping with NAXISn and
@@ -508,15 +513,15 @@ class BaseSpectralCube(object):
         if self.size >= MEMORY_THRESHOLD and not self.allow_huge_operations and not kwargs.pop('_allow_huge', True):
             raise ValueError("This function requires loading the whole cube into memory")      # utils.py:53-67
         yin, xin = self._pixel_map(newwcs, shape_out[1], shape_out[2])
-        out, foot = self._run_reproject(yin, xin, self._ORDERS[order], filled=filled)
-        if bool(torch.isnan(out).all()):
+        out, out32, foot, flag = self._run_reproject(yin, xin, self._ORDERS[order], filled=filled)
+        if int(flag.item()) == 0:
             raise ValueError("All values in reprojected cube are nan.  This can be caused"
                              " by an error in which coordinates do not 'round-trip'.  Try "
                              "setting ``roundtrip_coords=False``.  You might also check "
                              "whether the WCS transformation produces valid pixel->world "
                              "and world->pixel coordinates in each axis.")
         newmask = BooleanArrayMask(foot, wcs=newwcs)
-        cube = self._new_cube_with(data=out.to(torch.float32), wcs=newwcs, mask=newmask)
+        cube = self._new_cube_with(data=out32, wcs=newwcs, mask=newmask)
         cube._data_hi = out                        # reproject_interp returns float64
         cube._mask = newmask
         return cube
