@@ -201,7 +201,7 @@ reproject_tiled_kernel(const __grid_constant__ ReprojParams p, const __grid_cons
 
     // ---- per output pixel: neighbours and weights (consumers) ----
     const int64_t xo = (int64_t)blockIdx.x * RT + lane;
-    int64_t r0[RT_PX], c0[RT_PX];
+    int r0[RT_PX], c0[RT_PX];            // (image sides are far below 2^31)
     int dr[RT_PX], dc[RT_PX];            // r1 - r0, c1 - c0 (0 or 1)
     double w00[RT_PX], w01[RT_PX], w10[RT_PX], w11[RT_PX];
     bool outside[RT_PX];
@@ -220,22 +220,23 @@ reproject_tiled_kernel(const __grid_constant__ ReprojParams p, const __grid_cons
                     int64_t r1, c1;
                     if (p.order == 0) {
                         // nearest neighbour: scipy order 0 rounds half up
-                        r0[k] = r1 = min(max((int64_t)floor(ys + 0.5), (int64_t)0), p.ny_in - 1);
-                        c0[k] = c1 = min(max((int64_t)floor(xs + 0.5), (int64_t)0), p.nx_in - 1);
+                        r1 = min(max((int64_t)floor(ys + 0.5), (int64_t)0), p.ny_in - 1);
+                        c1 = min(max((int64_t)floor(xs + 0.5), (int64_t)0), p.nx_in - 1);
+                        r0[k] = (int)r1; c0[k] = (int)c1;
                         w00[k] = 1.0;
                     } else {
                         const double fy = floor(ys), fx = floor(xs);
                         const double wy1 = ys - fy, wy0 = 1.0 - wy1, wx1 = xs - fx, wx0 = 1.0 - wx1;
                         // edge-replicated padding: neighbours clamp to the image
-                        r0[k] = min(max((int64_t)fy, (int64_t)0), p.ny_in - 1);
+                        r0[k] = (int)min(max((int64_t)fy, (int64_t)0), p.ny_in - 1);
                         r1 = min(max((int64_t)fy + 1, (int64_t)0), p.ny_in - 1);
-                        c0[k] = min(max((int64_t)fx, (int64_t)0), p.nx_in - 1);
+                        c0[k] = (int)min(max((int64_t)fx, (int64_t)0), p.nx_in - 1);
                         c1 = min(max((int64_t)fx + 1, (int64_t)0), p.nx_in - 1);
                         w00[k] = wy0 * wx0; w01[k] = wy0 * wx1; w10[k] = wy1 * wx0; w11[k] = wy1 * wx1;
                     }
                     dr[k] = (int)(r1 - r0[k]); dc[k] = (int)(c1 - c0[k]);
-                    xmin = min(xmin, (int)c0[k]); xmax = max(xmax, (int)c1);
-                    ymin = min(ymin, (int)r0[k]); ymax = max(ymax, (int)r1);
+                    xmin = min(xmin, c0[k]); xmax = max(xmax, (int)c1);
+                    ymin = min(ymin, r0[k]); ymax = max(ymax, (int)r1);
                 }
             }
         }
@@ -280,7 +281,7 @@ reproject_tiled_kernel(const __grid_constant__ ReprojParams p, const __grid_cons
     if (fits) {
         int off[RT_PX];
 #pragma unroll
-        for (int k = 0; k < RT_PX; ++k) off[k] = outside[k] ? 0 : (int)(r0[k] - by0) * RT_BOX + (int)(c0[k] - bx0);
+        for (int k = 0; k < RT_PX; ++k) off[k] = outside[k] ? 0 : (r0[k] - by0) * RT_BOX + (c0[k] - bx0);
         for (int j = 0; j < nstage; ++j) {
             const int s = j % RT_STAGES;
             mbar_wait(&sm.full[s], (j / RT_STAGES) & 1);

@@ -187,6 +187,9 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     bool mprev[4] = {false, false, false, false}, mcur[4] = {false, false, false, false};
     bool any_included[4] = {false, false, false, false};
     int64_t jj = 0;
+    // the next LUT entry rides in registers, one entry ahead of the output it serves
+    InterpEntry enext = p.lut[0];
+    int32_t next_need = p.nchan_out > 0 ? enext.need : -1;
     for (int it = 0; it < n_iter; ++it) {
         const int s = it % IT_STAGES;
         const int64_t i0 = (int64_t)it * IT_CB;
@@ -205,9 +208,9 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
                 cd[k] = place_scaled_keep(cur[k]);
                 any_included[k] |= mcur[k];
             }
-            while (jj < p.nchan_out) {
-                const InterpEntry e = p.lut[jj];
-                if (e.need != (int32_t)i) break;
+            while (next_need == (int32_t)i) {                            // (the look-ahead keeps the LUT latency off this test)
+                const InterpEntry e = enext;
+                if (jj + 1 < p.nchan_out) { enext = p.lut[jj + 1]; next_need = enext.need; } else next_need = -1;
                 double r[4];
                 uint32_t mbits = 0;
 #pragma unroll
