@@ -96,7 +96,7 @@ const char *sc_last_error(void);
 int         sc_version(void);                 /* ABI version, currently 1 */
 /* Scratch a call may need, in bytes; op is one of the SC_OP_* below. */
 enum sc_op { SC_OP_MOMENTS = 1, SC_OP_SPECTRAL_SMOOTH = 2, SC_OP_SPATIAL_SMOOTH = 3,
-             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6 };
+             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6, SC_OP_REDUCE = 7 };
 size_t      sc_workspace_bytes(int op, int64_t nchan, int64_t ny, int64_t nx, int64_t aux);
 /* Number of kernel launches this library has enqueued in this process (all streams). */
 int64_t     sc_launch_count(void);
@@ -294,6 +294,23 @@ int sc_reproject_ex(const float *in, void *out, int out_dtype, float *out_f32, u
                     int64_t ny_out, int64_t nx_out,
                     const sc_mask_desc *mask, double fill,
                     const double *yin, const double *xin, int order, void *stream);
+
+/* ---- reductions along the spectral axis ------------------------------
+ * Replaces `apply_numpy_function(np.nansum / nanmean / nanstd / nanmax / nanmin / nanargmax /
+ * nanargmin, fill=..., axis=0)`: spectral_cube.py:361-470 (driver), `sum` :578-588, `mean` :592-652,
+ * `std` :669-724, `max` :770-781, `min` :785-796, `argmax` :800-811, `argmin` :815-826;
+ * dask_spectral_cube.py:641-767.  A voxel takes part iff the mask includes it and it is not NaN.
+ * One read of the cube serves every requested output (each (ny, nx), any may be NULL):
+ *   out_sum (f64; NaN when nothing takes part, np_compat.py:20-24), out_count (i32),
+ *   out_m2 (f64: sum of squared deviations from the mean; std = sqrt(m2 / (count - ddof))),
+ *   out_min / out_max (f32; NaN when nothing takes part), out_argmin / out_argmax (i32 channel of
+ *   the FIRST extremum like numpy; 0 when nothing takes part -- "arbitrary" in the reference).
+ */
+int sc_reduce_axis0(const float *cube, int64_t nchan, int64_t ny, int64_t nx,
+                    int64_t stride_c, int64_t stride_y, const sc_mask_desc *mask,
+                    double *out_sum, int32_t *out_count, double *out_m2,
+                    float *out_min, float *out_max, int32_t *out_argmin, int32_t *out_argmax,
+                    void *stream);
 
 /* Celestial pixel->pixel map for two TAN/SIN WCSs (the part of `reproject_interp` that
  * runs through astropy.wcs; FITS WCS papers I/II).  wcs_* = 12 doubles:

@@ -187,6 +187,34 @@ class OracleCube(object):
             return np.sum(psm[2 - axis, :] ** 2) ** 0.5
         raise ValueError("Cubes have 3 axes.")
 
+    # -- reductions (spectral_cube.py:361-470 `apply_numpy_function`, how='cube'; 578-826) -------------
+    def _apply_numpy_function(self, function, fill=np.nan, axis=None):
+        """spectral_cube.py:446-454: the function runs on the filled data of the whole cube."""
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return function(self._get_filled_data(fill=fill), axis=axis)
+
+    def sum(self, axis=None):
+        return self._apply_numpy_function(_mom.nansum_allbad_nan, axis=axis)            # :578-588 (np_compat.allbadtonan)
+
+    def mean(self, axis=None):
+        return self._apply_numpy_function(np.nanmean, axis=axis)                       # :650-652
+
+    def std(self, axis=None, ddof=0):
+        return self._apply_numpy_function(lambda a, axis: np.nanstd(a, axis=axis, ddof=ddof), axis=axis)   # :721-724
+
+    def max(self, axis=None):
+        return self._apply_numpy_function(np.nanmax, axis=axis)                        # :770-781
+
+    def min(self, axis=None):
+        return self._apply_numpy_function(np.nanmin, axis=axis)                        # :785-796
+
+    def argmax(self, axis=None):
+        return self._apply_numpy_function(np.nanargmax, fill=-np.inf, axis=axis)       # :800-811
+
+    def argmin(self, axis=None):
+        return self._apply_numpy_function(np.nanargmin, fill=np.inf, axis=axis)        # :815-826
+
     # -- moments -------------------------------------------------------------------------------
     def moment(self, order=0, axis=0, how='auto'):
         if axis == 0 and order == 2:

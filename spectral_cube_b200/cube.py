@@ -526,6 +526,77 @@ class BaseSpectralCube(object):
         cube._mask = newmask
         return cube
 
+    # -- reductions along the spectral axis (spectral_cube.py:361-470, 578-826; dask:641-767) ------------
+    def _reduce_axis0_raw(self, want):
+        """One pass over the cube for every requested statistic.  `want` is a set out of
+        {'sum', 'count', 'm2', 'min', 'max', 'argmin', 'argmax'}; returns name -> device tensor (ny, nx)."""
+        torch = _torch()
+        lib = _lib.load()
+        src = self._materialized()._data
+        nchan, ny, nx = self.shape
+        dev = src.device
+        dt = {'sum': torch.float64, 'count': torch.int32, 'm2': torch.float64, 'min': torch.float32,
+              'max': torch.float32, 'argmin': torch.int32, 'argmax': torch.int32}
+        outs = dict((k, torch.empty((ny, nx), dtype=dt[k], device=dev)) for k in want)
+        ptr = lambda k: outs[k].data_ptr() if k in outs else None
+        desc, keep = self._mask_desc()
+        _lib.check(lib.sc_reduce_axis0(src.data_ptr(), nchan, ny, nx, src.stride(0), src.stride(1), desc,
+                                       ptr('sum'), ptr('count'), ptr('m2'), ptr('min'), ptr('max'),
+                                       ptr('argmin'), ptr('argmax'), _stream()))
+        return outs
+
+    def _reduction_axis(self, axis, name):
+        if axis != 0:
+            raise NotImplementedError("%s(axis=%r): only reductions along the spectral axis (axis=0) run on the "
+                                      "device; see SURVEY.md 8(f)" % (name, axis))
+
+    def _collapsed(self, values, unit):
+        """Projection of a collapsed spectral axis (spectral_cube.py:395-414)."""
+        meta = {'collapse_axis': 0}
+        meta.update(self._meta)
+        return Projection(values, unit=unit, wcs=self._wcs.drop_axis(0), meta=meta, header=self._header, copy=False)
+
+    def _np_dtype(self):
+        return np.float32          # the cube's dtype: the nan-functions of the reference keep it
+
+    def sum(self, axis=None, how='auto', **kwargs):
+        """Sum over the spectral axis; spaxels with nothing included are NaN (np_compat.allbadtonan)."""
+        self._reduction_axis(axis, 'sum')
+        r = self._reduce_axis0_raw({'sum'})
+        return self._collapsed(r['sum'].cpu().numpy().astype(self._np_dtype()), self._unit)
+
+    def mean(self, axis=None, how='cube', **kwargs):
+        self._reduction_axis(axis, 'mean')
+        r = self._reduce_axis0_raw({'sum', 'count'})
+        torch = _torch()
+        out = r['sum'] / r['count'].to(torch.float64)            # 0 / 0 never happens: sum is NaN there
+        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
+
+    def std(self, axis=None, how='cube', ddof=0, **kwargs):
+        self._reduction_axis(axis, 'std')
+        r = self._reduce_axis0_raw({'m2', 'count'})
+        torch = _torch()
+        n = r['count'].to(torch.float64) - float(ddof)
+        out = torch.sqrt(r['m2'] / torch.where(n > 0, n, torch.full_like(n, float('nan'))))
+        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
+
+    def max(self, axis=None, how='auto', **kwargs):
+        self._reduction_axis(axis, 'max')
+        return self._collapsed(self._reduce_axis0_raw({'max'})['max'].cpu().numpy(), self._unit)
+
+    def min(self, axis=None, how='auto', **kwargs):
+        self._reduction_axis(axis, 'min')
+        return self._collapsed(self._reduce_axis0_raw({'min'})['min'].cpu().numpy(), self._unit)
+
+    def argmax(self, axis=None, how='auto', **kwargs):
+        """Channel of the (first) maximum; arbitrary (0) where nothing is included (spectral_cube.py:800-811)."""
+        self._reduction_axis(axis, 'argmax')
+        return self._reduce_axis0_raw({'argmax'})['argmax'].cpu().numpy().astype(np.int64)
+
+    def argmin(self, axis=None, how='auto', **kwargs):
+        self._reduction_axis(axis, 'argmin')
+        return self._reduce_axis0_raw({'argmin'})['argmin'].cpu().numpy().astype(np.int64)
+
     # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
     def _moments_axis0_raw(self, want_bits):
         """Run the fused kernel; returns dict order -> float64 device tensor (ny, nx), with units

@@ -1,0 +1,113 @@
+"""
+GPU parity tests for the spectral-axis reductions (``-m gpu``): `sum`, `mean`, `std`, `max`, `min`,
+`argmax`, `argmin` against the oracle restatement of `apply_numpy_function` (numpy's nan-functions
+on the mask-filled cube, spectral_cube.py:361-470 and :578-826) and the reference's own checks
+(spectral_cube/tests/test_spectral_cube.py: `test_sum`/`test_max`/`test_argmax`... compare with numpy
+on the filled data).  Tolerance: exact for extrema and indices; 1e-5 relative for sum / mean / std,
+with an absolute floor of 1e-5 x the spaxel's sum of |values| for the float32-accumulating numpy sum
+(the product accumulates in float64 and rounds once).
+"""
+import warnings
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_cube, gpu_cube, assert_maps_close, RTOL
+from tests.test_moments_gpu import BENCH_WCS, MASKS, _random_cube
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(shape, maskname, seed_extra=''):
+    data = _random_cube(shape, seed=zlib.crc32(repr((shape, maskname, seed_extra)).encode()))
+    sc, oc = gpu_cube(data, BENCH_WCS), oracle_cube(data, BENCH_WCS)
+    ms, mo = MASKS[maskname](sc), MASKS[maskname](oc)
+    if ms is not None:
+        sc, oc = sc.with_mask(ms), oc.with_mask(mo)
+    return data, sc, oc
+
+
+@pytest.mark.parametrize('maskname', sorted(MASKS))
+@pytest.mark.parametrize('shape', [(32, 9, 16), (33, 7, 13), (40, 5, 6)])
+def test_reductions_match_oracle_under_lazy_masks(shape, maskname):
+    data, sc, oc = _pair(shape, maskname)
+    inc = oc._mask_include() & ~np.isnan(data)
+    scale = np.where(inc, np.abs(data), 0).sum(axis=0).astype(np.float64)      # sum of |values| per spaxel
+    for name in ('sum', 'mean', 'std'):
+        got = getattr(sc, name)(axis=0)
+        want = getattr(oc, name)(axis=0)
+        assert got.value.dtype == np.float32 and got.unit == 'K' and got.meta['collapse_axis'] == 0
+        gn, wn = np.isnan(got.value), np.isnan(want)
+        np.testing.assert_array_equal(gn, wn, err_msg=name)
+        ok = ~wn
+        div = 1.0 if name == 'sum' else np.maximum(inc.sum(axis=0), 1)
+        tol = RTOL * np.abs(want[ok]) + RTOL * (scale / div)[ok]
+        assert (np.abs(got.value[ok].astype(np.float64) - want[ok]) <= tol).all(), name
+    for name in ('max', 'min'):
+        got = getattr(sc, name)(axis=0)
+        want = getattr(oc, name)(axis=0)
+        np.testing.assert_array_equal(got.value, want, err_msg=name)               # exact, NaN where nothing is included
+    any_inc = inc.any(axis=0)
+    for name in ('argmax', 'argmin'):
+        got = getattr(sc, name)(axis=0)
+        assert got.dtype == np.int64
+        # all-excluded spaxels are "arbitrary" in the reference (and all-NaN ones raise in numpy): compare the rest
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            fill = -np.inf if name == 'argmax' else np.inf
+            filled = np.where(inc, data, fill)
+            want = getattr(np, name)(filled, axis=0)
+        np.testing.assert_array_equal(got[any_inc], want[any_inc], err_msg=name)
+        assert (got[~any_inc] == 0).all()
+
+
+def test_std_ddof_and_variance_without_cancellation():
+    rng = np.random.default_rng(11)
+    data = (1.0e4 + rng.normal(0, 1e-2, (64, 8, 12))).astype(np.float32)            # mean >> spread
+    sc, oc = gpu_cube(data, BENCH_WCS), oracle_cube(data, BENCH_WCS)
+    for ddof in (0, 1):
+        want = np.nanstd(data.astype(np.float64), axis=0, ddof=ddof)               # the exact answer
+        got = sc.std(axis=0, ddof=ddof).value
+        np.testing.assert_allclose(got, want, rtol=1e-5)
+
+
+def test_first_occurrence_and_ties():
+    data = np.zeros((6, 4, 4), dtype=np.float32)
+    data[2] = 5.0; data[4] = 5.0; data[1] = -3.0; data[5] = -3.0
+    sc = gpu_cube(data, BENCH_WCS)
+    assert (sc.argmax(axis=0) == 2).all() and (sc.argmin(axis=0) == 1).all()
+    assert (sc.max(axis=0).value == 5.0).all() and (sc.min(axis=0).value == -3.0).all()
+
+
+def test_only_the_spectral_axis_runs_on_the_device():
+    sc = gpu_cube(np.ones((4, 4, 4), dtype=np.float32), BENCH_WCS)
+    with pytest.raises(NotImplementedError):
+        sc.sum(axis=1)
+
+
+def test_peak_and_noise_maps_at_scale():
+    """docs/examples.rst:61-93 at bench scale: size-independent properties of one pass."""
+    import torch
+    from spectral_cube_b200.synth import synth_cube
+    import spectral_cube_b200 as scb
+    nchan, ny, nx = 256, 512, 1024
+    dev = synth_cube(nchan, ny, nx, border=8)
+    cube = gpu_cube(dev, dict(BENCH_WCS, crpix=[nx / 2 + 0.5, ny / 2 + 0.5, 1.0]))
+    r = cube._reduce_axis0_raw({'sum', 'count', 'm2', 'min', 'max', 'argmin', 'argmax'})
+    cnt = r['count']
+    fin = torch.isfinite(dev)
+    assert torch.equal(cnt, fin.sum(dim=0).to(torch.int32))
+    ok = cnt > 0
+    filled_hi = torch.where(fin, dev, torch.full_like(dev, -float('inf')))
+    filled_lo = torch.where(fin, dev, torch.full_like(dev, float('inf')))
+    assert torch.equal(r['max'][ok], filled_hi.max(dim=0).values[ok])
+    assert torch.equal(r['min'][ok], filled_lo.min(dim=0).values[ok])
+    # the value at the reported channel IS the extremum
+    gathered = torch.gather(dev, 0, r['argmax'].to(torch.int64)[None])[0]
+    assert torch.equal(gathered[ok], r['max'][ok])
+    # linearity of the sum: sum(2 x) == 2 sum(x) exactly in binary floating point
+    r2 = gpu_cube(dev * 2, dict(BENCH_WCS, crpix=[nx / 2 + 0.5, ny / 2 + 0.5, 1.0]))._reduce_axis0_raw({'sum', 'm2'})
+    assert torch.equal(r2['sum'][ok], 2 * r['sum'][ok])
+    assert torch.allclose(r2['m2'][ok], 4 * r['m2'][ok], rtol=1e-12)
+    assert torch.isnan(r['sum'][~ok]).all() and torch.isnan(r['max'][~ok]).all()

@@ -165,6 +165,20 @@ if 'c5' in which:
              (4 + 9) * nout * ny * nx)
         emit('c5', 'config 5 total: spectral_interpolate + reproject', V, ms_i + ms_r, 0)
 
+if 'reduce' in which and world == 1:
+    # the noise / peak maps behind a ">3 sigma" mask, one pass for all seven statistics
+    nchan, ny, nx = 1024, 2048, 2048
+    V = nchan * ny * nx
+    dev = synth_cube(nchan, ny, nx, border=51)
+    c = isfinite_cube(scb.SpectralCube, dev, benchmark_wcs(nchan, ny, nx))
+    allstats = {'sum', 'count', 'm2', 'min', 'max', 'argmin', 'argmax'}
+    ms = timeit(lambda: c._reduce_axis0_raw(allstats))
+    emit('reduce', 'sum+count+m2+min+max+argmin+argmax along the spectral axis in one pass, 2048x2048x1024', V, ms, 4 * V + 36 * ny * nx)
+    ms = timeit(lambda: c._reduce_axis0_raw({'max'}))
+    emit('reduce', 'max along the spectral axis (peak map)', V, ms, 4 * V + 4 * ny * nx)
+    del dev, c
+    torch.cuda.empty_cache()
+
 if 'target' in which:
     # north-star target: moment0/1/2 + spectral_smooth on the 4096x4096x2048 cube.  One GPU holds the whole
     # 137.4 GB cube (smoothing runs in place); N GPUs hold 1/N of the rows each.
