@@ -228,6 +228,25 @@ int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
                           int plane_passthrough,
                           void *workspace, size_t workspace_bytes, void *stream);
 
+/* Denominator strategy of the separable path.  `sc_spatial_smooth_sep` samples the cube itself (every
+ * 8th row of up to 16 planes) and lets the device pick between the sparse integer deficit (few missing
+ * samples) and the convolved float32 denominator (more than 10 % missing).  A row-sharded job must take
+ * ONE decision for all shards to stay bit-identical with the unsharded result: each rank calls
+ * `sc_spatial_missing_sample` (counts = device uint32[2] {missing, sampled}, accumulated, not zeroed),
+ * sums the counts over the ranks and hands them to `sc_spatial_smooth_sep_ex`. */
+int sc_spatial_missing_sample(const float *in, int64_t nchan, int64_t ny, int64_t nx,
+                              int64_t stride_c, int64_t stride_y, const sc_mask_desc *mask,
+                              unsigned int *counts, void *stream);
+int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtype,
+                             int64_t nchan, int64_t ny, int64_t nx,
+                             int64_t stride_c, int64_t stride_y,
+                             int64_t out_stride_c, int64_t out_stride_y,
+                             const sc_mask_desc *mask, double fill,
+                             const double *taps_y, int ntaps_y, const double *taps_x, int ntaps_x,
+                             const float *halo_top, const float *halo_bot, int halo_rows,
+                             int plane_passthrough, const unsigned int *strategy_counts,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
                          int64_t nchan, int64_t ny, int64_t nx,
                          int64_t stride_c, int64_t stride_y,

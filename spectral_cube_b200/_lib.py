@@ -66,6 +66,9 @@ SIGNATURES = {
                                        _pd, _dbl, _dbl, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'sc_spatial_smooth_sep': (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
                                      _pd, _i32, _pd, _i32, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
+    'sc_spatial_smooth_sep_ex': (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
+                                        _pd, _i32, _pd, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    'sc_spatial_missing_sample': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _pmask, _vp, _vp]),
     'sc_spatial_smooth_2d': (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
                                     _pd, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     'sc_pack_filled_rows': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl, _i64, _i64, _vp, _vp]),

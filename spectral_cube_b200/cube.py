@@ -367,7 +367,19 @@ class BaseSpectralCube(object):
             return ky, kx
         return None
 
-    def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0):
+    def _spatial_strategy_counts(self):
+        """Device uint32[2] {missing, sampled} of this cube's rows: what the separable spatial kernels use to
+        pick their denominator strategy.  Row-sharded jobs sum it over the ranks (distributed.py)."""
+        torch = _torch()
+        lib = _lib.load()
+        src = self._data
+        counts = torch.zeros((2,), dtype=torch.int32, device=src.device)
+        desc, keep = self._mask_desc()
+        _lib.check(lib.sc_spatial_missing_sample(src.data_ptr(), *self.shape, src.stride(0), src.stride(1), desc,
+                                                 counts.data_ptr(), _stream()))
+        return counts
+
+    def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0, strategy_counts=None):
         torch = _torch()
         lib = _lib.load()
         src = self._data
@@ -384,8 +396,9 @@ class BaseSpectralCube(object):
         sep = self._separable_factors(k2d)
         if sep is not None:
             (ya, yp), (xa, xp) = _lib.as_double_array(sep[0]), _lib.as_double_array(sep[1])
-            _lib.check(lib.sc_spatial_smooth_sep(*common, yp, len(ya), xp, len(xa), ht, hb, int(halo_rows), passthrough,
-                                                 ws.data_ptr(), ws.numel(), _stream()))
+            sc = strategy_counts.data_ptr() if strategy_counts is not None else None
+            _lib.check(lib.sc_spatial_smooth_sep_ex(*common, yp, len(ya), xp, len(xa), ht, hb, int(halo_rows), passthrough,
+                                                    sc, ws.data_ptr(), ws.numel(), _stream()))
         else:
             ka, kp = _lib.as_double_array(k2d.ravel())
             _lib.check(lib.sc_spatial_smooth_2d(*common, kp, k2d.shape[0], k2d.shape[1], ht, hb, int(halo_rows), passthrough,

@@ -239,7 +239,14 @@ class RowShardedCube(object):
         if h > 0:
             halo_top, halo_bot = exchange_halo_rows(pack(0), pack(ny - h), self.group, mode=halo_mode)
         dask = loc._mirrors_dask
-        out = loc._run_spatial_smooth(k2d, _lib.F32 if dask else _lib.F64, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h)
+        # one denominator strategy for the whole job (bit-identical with the unsharded result): the ranks'
+        # sample counts are summed (8 bytes; the only other exchange of this op are the halo rows)
+        counts = loc._spatial_strategy_counts()
+        dist = _dist()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        out = loc._run_spatial_smooth(k2d, _lib.F32 if dask else _lib.F64, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h,
+                                      strategy_counts=counts)
         new = loc._new_cube_with(data=out) if dask else loc._new_cube_from_f64(out)
         return self._wrap(new)
 

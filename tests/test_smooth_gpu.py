@@ -189,6 +189,24 @@ def test_spatial_smooth_gaussian_matches_oracle(sigma, use_dask):
     assert_maps_close(got, want, rtol=RTOL, what='sigma=%g' % sigma)
 
 
+@pytest.mark.parametrize('sigma', [1.0, 8 / 2.3548200450309493])
+def test_spatial_smooth_blank_bands_and_crowded_blocks(sigma):
+    """The three denominator paths of the sparse separable kernel in one image: isolated NaNs (listed
+    inputs), a half-masked region (crowded blocks: integer convolution of the flags) and a blank band
+    wider than a CTA's 8 x 160 window (closed form; outputs deep inside keep the filled input)."""
+    scb = _kernels()
+    rng = np.random.default_rng(int(sigma * 100))
+    data = _random_cube((2, 96, 640), seed=int(sigma * 7), nan_frac=0.002)
+    data[:, 24:72, 90:520] = np.nan                                           # blank band
+    speckle = rng.random((2, 20, 300)) < 0.5
+    data[:, 74:94, 200:500][speckle] = np.nan                                 # crowded, not blank
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=True), oracle_cube(data, BENCH_WCS, use_dask=True)
+    got = sc.spatial_smooth(scb.Gaussian2DKernel(sigma)).unmasked_data[:]
+    want = oc.spatial_smooth(oconv.Gaussian2DKernel(sigma))._data
+    assert np.isnan(want[:, 45:50, 200:400]).all()                            # deep inside the band: nothing valid
+    assert_maps_close(got, want, rtol=RTOL, what='sigma=%g' % sigma)
+
+
 def test_spatial_smooth_elliptical_and_nonseparable_match_oracle():
     scb = _kernels()
     data = _random_cube((2, 40, 64), seed=77, nan_frac=0.02)
@@ -236,7 +254,10 @@ def test_spatial_smooth_row_shards_with_halos_equal_the_whole_image():
         return out
     halo_for_top = pack(bot, 0, h)                       # the rows just below the top shard
     halo_for_bot = pack(top, 40 - h, h)                  # the rows just above the bottom shard
-    a = top._run_spatial_smooth(k.array, _lib.F32, halo_top=None, halo_bot=halo_for_top, halo_rows=h)
-    b = bot._run_spatial_smooth(k.array, _lib.F32, halo_top=halo_for_bot, halo_bot=None, halo_rows=h)
+    # one denominator strategy for all shards: the job-wide sample (here: the shards' counts summed)
+    counts = top._spatial_strategy_counts() + bot._spatial_strategy_counts()
+    assert torch.equal(counts, whole._spatial_strategy_counts())          # 40 rows: both shards start on a sampled row
+    a = top._run_spatial_smooth(k.array, _lib.F32, halo_top=None, halo_bot=halo_for_top, halo_rows=h, strategy_counts=counts)
+    b = bot._run_spatial_smooth(k.array, _lib.F32, halo_top=halo_for_bot, halo_bot=None, halo_rows=h, strategy_counts=counts)
     got = torch.cat([a, b], dim=1)
     assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
