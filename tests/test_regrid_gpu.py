@@ -235,3 +235,29 @@ def test_reproject_refuses_all_nan_result():
     hdr['CRVAL1'] += 5.0                                   # five degrees away: no overlap
     with pytest.raises(ValueError, match="All values in reprojected cube are nan"):
         cube.reproject(hdr)
+
+
+def test_reproject_identity_and_integer_shift_at_scale():
+    """Size-independent properties of the tiled kernel on a plane far larger than its tiles: reprojecting
+    onto the cube's own header returns the data (the pixel map goes through the sphere, so the weights are
+    1 - O(1e-12) and O(1e-12): 1e-6 relative), onto a header shifted by whole pixels returns the shifted
+    data, and everything mapped from outside the image is NaN with a False footprint."""
+    import torch
+    from spectral_cube_b200.synth import synth_cube, benchmark_wcs
+    import spectral_cube_b200 as scb
+    nchan, ny, nx = 6, 1024, 2048
+    dev = synth_cube(nchan, ny, nx, border=0, nan_permille=0)
+    w = benchmark_wcs(nchan, ny, nx)
+    cube = scb.SpectralCube(dev, w, unit='K')
+    same = cube.reproject(w, shape_out=(nchan, ny, nx))
+    assert torch.allclose(same._data, dev, rtol=1e-6, atol=1e-6)
+    assert bool(same._mask.include().all())
+    w2 = w.copy()
+    w2.crpix[0] += 7          # output pixel (x, y) looks at input pixel (x - 7, y + 5)
+    w2.crpix[1] -= 5
+    shifted = cube.reproject(w2, shape_out=(nchan, ny, nx))
+    got = shifted._data
+    assert torch.allclose(got[:, :ny - 5, 7:], dev[:, 5:, :nx - 7], rtol=1e-6, atol=1e-6)
+    assert bool(torch.isnan(got[:, ny - 4:, :]).all()) and bool(torch.isnan(got[:, :, :6]).all())
+    inc = shifted._mask.include()
+    assert not inc[:, ny - 4:, :].any() and inc[:, :ny - 5, 7:].all()
