@@ -31,17 +31,24 @@ struct LaunchScope {
 // MODE_INTERVAL: isfinite(self) [& self OP scalar] -> include = lo < v && v < hi  (float32
 //                bounds chosen on the host so the test equals (double)v OP thr exactly)
 // MODE_GENERIC:  anything else: interpret the node list.
-enum { MODE_NONE = 0, MODE_INTERVAL = 1, MODE_GENERIC = 2 };
+// MODE_INTERVAL_OTHER: the same interval test on ANOTHER cube's voxel (the mask a smoothed cube keeps:
+//                built on the data it was smoothed from, spectral_cube.py:3043-3045).  Kernels without a
+//                dedicated path treat it as MODE_GENERIC (the node program is always carried).
+enum { MODE_NONE = 0, MODE_INTERVAL = 1, MODE_GENERIC = 2, MODE_INTERVAL_OTHER = 3 };
 
 struct DevMask {
     int   mode;
     float lo, hi;
+    const float *other;    // MODE_INTERVAL_OTHER: the cube the interval is tested on, and its strides
+    int64_t other_sc, other_sy;
     sc_mask_desc prog;     // only read in MODE_GENERIC
 };
 
 // Host: classify a descriptor.  Returns SC_OK or an error.
+// `allow_other`: the caller has a MODE_INTERVAL_OTHER path (only the moment kernels do); everyone else
+// gets MODE_GENERIC for masks that live on another cube.
 int build_dev_mask(const sc_mask_desc *m, const float *cube, int64_t stride_c, int64_t stride_y,
-                   DevMask *out);
+                   DevMask *out, bool allow_other = false);
 // Host: true if any node references memory other than the cube itself.
 bool mask_is_self_only(const sc_mask_desc *m);
 

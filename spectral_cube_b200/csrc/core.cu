@@ -97,7 +97,12 @@ static bool node_is_self(const sc_mask_node &nd, const float *cube, int64_t sc, 
 // Fold FINITE / CMP_SCALAR(GT,GE,LT,LE) on the cube itself joined by AND into one open
 // float32 interval (lo, hi).  Returns false if the subtree is anything else.
 static bool fold_interval(const sc_mask_desc *m, int i, const float *cube, int64_t sc, int64_t sy,
-                          float *lo, float *hi) {
+                          float *lo, float *hi, bool other = false) {
+    // other = true: `cube` is a cube that is NOT the one being processed; leaves must reference exactly it
+    auto node_is_self = [other](const sc_mask_node &n, const float *cb, int64_t c, int64_t y) {
+        if (other) return n.data == cb && n.ds_c == c && n.ds_y == y;
+        return n.data == nullptr || (n.data == cb && n.ds_c == c && n.ds_y == y);
+    };
     const sc_mask_node &nd = m->nodes[i];
     switch (nd.kind) {
         case SC_MASK_FINITE:
@@ -116,7 +121,7 @@ static bool fold_interval(const sc_mask_desc *m, int i, const float *cube, int64
             return true;
         }
         case SC_MASK_AND:
-            return fold_interval(m, nd.a, cube, sc, sy, lo, hi) && fold_interval(m, nd.b, cube, sc, sy, lo, hi);
+            return fold_interval(m, nd.a, cube, sc, sy, lo, hi, other) && fold_interval(m, nd.b, cube, sc, sy, lo, hi, other);
         default:
             return false;
     }
@@ -130,7 +135,7 @@ static bool subtree_has_finite(const sc_mask_desc *m, int i) {
 }
 
 int build_dev_mask(const sc_mask_desc *m, const float *cube, int64_t stride_c, int64_t stride_y,
-                   DevMask *out) {
+                   DevMask *out, bool allow_other) {
     memset(out, 0, sizeof(*out));
     if (m == nullptr || m->n_nodes == 0) { out->mode = MODE_NONE; return SC_OK; }
     SC_CHECK_ARG(m->n_nodes > 0 && m->n_nodes <= SC_MASK_MAX_NODES, "mask: n_nodes=%d out of range", m->n_nodes);
@@ -163,6 +168,18 @@ int build_dev_mask(const sc_mask_desc *m, const float *cube, int64_t stride_c, i
     if (subtree_has_finite(m, root) && fold_interval(m, root, cube, stride_c, stride_y, &lo, &hi)) {
         out->mode = MODE_INTERVAL; out->lo = lo; out->hi = hi;
         return SC_OK;
+    }
+    // the same conjunction on another cube (a smoothed cube under the mask of its source)
+    for (int i = 0; allow_other && i < m->n_nodes; ++i) {
+        const sc_mask_node &nd = m->nodes[i];
+        if (nd.kind > SC_MASK_CMP_SCALAR || nd.data == nullptr || node_is_self(nd, cube, stride_c, stride_y)) continue;
+        lo = -INFINITY; hi = INFINITY;
+        if (subtree_has_finite(m, root) && fold_interval(m, root, nd.data, nd.ds_c, nd.ds_y, &lo, &hi, true)) {
+            out->mode = MODE_INTERVAL_OTHER; out->lo = lo; out->hi = hi;
+            out->other = nd.data; out->other_sc = nd.ds_c; out->other_sy = nd.ds_y;
+            return SC_OK;
+        }
+        break;
     }
     out->mode = MODE_GENERIC;
     out->prog = *m;

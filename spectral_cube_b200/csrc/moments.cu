@@ -46,9 +46,13 @@ struct MomParams {
 // NaN voxels never touch the float64 results; no select instructions are needed).
 template <int MODE, int WANT>
 __device__ __forceinline__ void accumulate(const DevMask &m, float f, int64_t c, int64_t y, int64_t x,
-                                           const double2 &t, double &s0, double &s1, double &s2, int &cnt) {
-    bool inc = mask_include<MODE>(m, f, c, y, x);
-    if (MODE != MODE_INTERVAL) inc = inc & (f == f);
+                                           const double2 &t, double &s0, double &s1, double &s2, int &cnt, float other = 0.0f) {
+    bool inc;
+    if (MODE == MODE_INTERVAL_OTHER) inc = (other > m.lo) & (other < m.hi) & (f == f);   // the mask lives on another cube
+    else {
+        inc = mask_include<(MODE == MODE_INTERVAL_OTHER ? MODE_GENERIC : MODE)>(m, f, c, y, x);
+        if (MODE != MODE_INTERVAL) inc = inc & (f == f);
+    }
     if (inc) {
         const double w = (double)f;
         s0 += w;
@@ -199,31 +203,40 @@ moments_axis0_kernel(const __grid_constant__ MomParams p) {
         const int64_t c_begin = (int64_t)sy * chunk;
         const int64_t c_end = min(p.nchan, c_begin + chunk);
         const float *ptr = p.cube + y * p.stride_y + x + c_begin * p.stride_c;
+        constexpr bool OTHER = MODE == MODE_INTERVAL_OTHER;     // a second stream: the cube the mask is tested on
+        const float *optr = OTHER ? p.mask.other + y * p.mask.other_sy + x + c_begin * p.mask.other_sc : ptr;
+        const int64_t ostep = OTHER ? p.mask.other_sc : 0;
 
         int64_t c = c_begin;
         for (; c + UNROLL <= c_end; c += UNROLL) {
-            float v[UNROLL][VEC];
+            float v[UNROLL][VEC], ov[OTHER ? UNROLL : 1][VEC];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) VecLoad<VEC>::load(ptr + (int64_t)u * p.stride_c, v[u]);
+            for (int u = 0; u < UNROLL; ++u) {
+                VecLoad<VEC>::load(ptr + (int64_t)u * p.stride_c, v[u]);
+                if (OTHER) VecLoad<VEC>::load(optr + (int64_t)u * ostep, ov[OTHER ? u : 0]);
+            }
             ptr += (int64_t)UNROLL * p.stride_c;
+            optr += (int64_t)UNROLL * ostep;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 double2 t = make_double2(0.0, 0.0);
                 if (WANT & (SC_WANT_M1 | SC_WANT_M2)) t = __ldg(p.tab + c + u);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    accumulate<MODE, WANT>(p.mask, v[u][j], c + u, y, x + j, t, s0[j], s1[j], s2[j], cnt[j]);
+                    accumulate<MODE, WANT>(p.mask, v[u][j], c + u, y, x + j, t, s0[j], s1[j], s2[j], cnt[j], OTHER ? ov[OTHER ? u : 0][j] : 0.0f);
             }
         }
         for (; c < c_end; ++c) {
-            float v[VEC];
+            float v[VEC], ov[VEC];
             VecLoad<VEC>::load(ptr, v);
+            if (OTHER) VecLoad<VEC>::load(optr, ov);
             ptr += p.stride_c;
+            optr += ostep;
             double2 t = make_double2(0.0, 0.0);
             if (WANT & (SC_WANT_M1 | SC_WANT_M2)) t = __ldg(p.tab + c);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                accumulate<MODE, WANT>(p.mask, v[j], c, y, x + j, t, s0[j], s1[j], s2[j], cnt[j]);
+                accumulate<MODE, WANT>(p.mask, v[j], c, y, x + j, t, s0[j], s1[j], s2[j], cnt[j], OTHER ? ov[j] : 0.0f);
         }
     }
 
@@ -320,6 +333,7 @@ static cudaError_t launch_moments_mode(const MomParams &p, int want, dim3 grid, 
     switch (p.mask.mode) {
         case MODE_NONE:     return launch_moments_want<VEC, UNROLL, MODE_NONE>(p, want, grid, block, smem, s);
         case MODE_INTERVAL: return launch_moments_want<VEC, UNROLL, MODE_INTERVAL>(p, want, grid, block, smem, s);
+        case MODE_INTERVAL_OTHER: return launch_moments_want<VEC, UNROLL, MODE_INTERVAL_OTHER>(p, want, grid, block, smem, s);
         default:            return launch_moments_want<VEC, UNROLL, MODE_GENERIC>(p, want, grid, block, smem, s);
     }
 }
@@ -372,7 +386,7 @@ int moments_axis0_device(const float *cube, int64_t nchan, int64_t ny, int64_t n
     p.tab = tab_dev; p.K = K; p.pix_size = pix_size; p.m1_offset = m1_offset;
     p.m0 = out_m0; p.m1 = out_m1; p.m2 = out_m2;
     p.tiles_per_row = 0; p.groups_per_row = 0; p.ngroups = 0;
-    int rc = build_dev_mask(mask, cube, stride_c, stride_y, &p.mask);
+    int rc = build_dev_mask(mask, cube, stride_c, stride_y, &p.mask, true);
     if (rc != SC_OK) return rc;
 
     if (want_bits & (SC_WANT_M1 | SC_WANT_M2)) {
@@ -388,7 +402,11 @@ int moments_axis0_device(const float *cube, int64_t nchan, int64_t ny, int64_t n
     const int64_t tiles_per_row = cdiv(nx, TMA_TILE_X);
     const int64_t n_tiles = tiles_per_row * ny;
     const int kernel_choice = env_int("SC_MOM_KERNEL", 0);      // 0 auto, 1 direct, 2 tma
-    const bool tma_ok = al16 && n_tiles < (int64_t)1 << 31;
+    // a mask on another cube streams that cube too: the direct kernel reads both (the TMA ring carries one cube)
+    const bool other = p.mask.mode == MODE_INTERVAL_OTHER;
+    const bool oal16 = !other || (((uintptr_t)p.mask.other % 16 == 0) && p.mask.other_sc % 4 == 0 && p.mask.other_sy % 4 == 0);
+    const bool oal8 = !other || (((uintptr_t)p.mask.other % 8 == 0) && p.mask.other_sc % 2 == 0 && p.mask.other_sy % 2 == 0);
+    const bool tma_ok = al16 && !other && n_tiles < (int64_t)1 << 31;
     if (tma_ok && kernel_choice != 1 && (kernel_choice == 2 || n_tiles >= 2 * 148 * 3)) {
         p.tiles_per_row = (int)tiles_per_row;
         const int cfg = env_int("SC_MOM_TMA_CFG", 0);
@@ -406,7 +424,7 @@ int moments_axis0_device(const float *cube, int64_t nchan, int64_t ny, int64_t n
 
     // ---- direct-load path ----
     int vec = 1;
-    if (al16) vec = 4; else if (al8) vec = 2;
+    if (al16 && oal16) vec = 4; else if (al8 && oal8) vec = 2;
     int force_vec = env_int("SC_MOM_VEC", 0);
     if (force_vec == 1 || (force_vec == 2 && al8)) vec = force_vec;
     p.groups_per_row = nx / vec;

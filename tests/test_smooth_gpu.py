@@ -124,6 +124,25 @@ def test_smooth_then_moment_fused_matches_oracle(kernel_path, monkeypatch):
                           rtol=1e-9, atol=1e-9, what='materialised vs fused %d' % order)
 
 
+@pytest.mark.parametrize('use_dask', [False, True])
+@pytest.mark.parametrize('shape', [(64, 6, 64), (40, 5, 13)])
+def test_moments_of_a_smoothed_cube_under_the_mask_of_its_source(shape, use_dask):
+    """The mask object survives smoothing untouched (spectral_cube.py:3043-3045): a `> threshold` LazyMask keeps
+    testing the ORIGINAL data while the moments sum the smoothed data.  The materialised route streams both
+    cubes (interval test on the other cube); odd widths take the scalar loads."""
+    scb = _kernels()
+    data = _random_cube(shape, seed=shape[2], nan_frac=0.02) + np.float32(2.0)
+    sc, oc = gpu_cube(data, BENCH_WCS, use_dask=use_dask), oracle_cube(data, BENCH_WCS, use_dask=use_dask)
+    sc, oc = sc.with_mask(sc > 3.0), oc.with_mask(oc > 3.0)
+    k = 5 / 2.3548200450309493
+    kw = dict(save_to_tmp_dir=True) if use_dask else {}
+    ssm, osm = sc.spectral_smooth(scb.Gaussian1DKernel(k), **kw), oc.spectral_smooth(oconv.Gaussian1DKernel(k))
+    for order in (0, 1, 2):
+        got = quiet(ssm.moment, order=order).value
+        want = quiet(osm.moment, order=order)[0]
+        assert_maps_close(got, want, rtol=RTOL, atol=1e-6 if order == 2 else 0.0, what='moment%d' % order)
+
+
 def test_smoothing_is_linear_and_preserves_constants_at_scale():
     """Size-independent properties on a 512 x 256 x 2048 cube (1 GB): a constant cube stays constant
     away from the spectral edges; smoothing 2x the data gives 2x the result exactly."""
