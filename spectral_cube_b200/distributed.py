@@ -245,9 +245,9 @@ class RowShardedCube(object):
         dist = _dist()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
-        out = loc._run_spatial_smooth(k2d, _lib.F32 if dask else _lib.F64, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h,
+        out = loc._run_spatial_smooth(k2d, _lib.F32, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h,
                                       strategy_counts=counts)
-        new = loc._new_cube_with(data=out) if dask else loc._new_cube_from_f64(out)
+        new = loc._new_cube_with(data=out) if dask else loc._new_cube_reporting_f64(out)
         return self._wrap(new)
 
     # ---- reproject: one re-shard to channels, then whole planes locally -------------------------------
