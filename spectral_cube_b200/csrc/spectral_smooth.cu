@@ -7,9 +7,9 @@
 // VALID samples, out = sum_k K[k] v[c-k] [v not NaN] / sum_k K[k] [v not NaN] in float64,
 // denominator 0 keeps the input value.  Masked voxels are replaced by `fill` before convolving.
 //
-// Kernel (smooth_tma_kernel).  A CTA owns SM_TILE adjacent spaxels of one image row, one per
-// thread.  Blocks of B channels x SM_TILE floats (one `cp.async.bulk` / TMA row copy of 1 KB per
-// channel) stream through a STAGES-deep shared-memory ring; arrival is an mbarrier per slot, and
+// Kernel (smooth_tma_kernel).  A CTA owns SM_TILE (128) adjacent spaxels of one image row, one per
+// thread.  Blocks of B channels x SM_TILE floats (one tiled TMA request per block,
+// `cp.async.bulk.tensor.3d`) stream through a STAGES-deep shared-memory ring; arrival is an mbarrier per slot, and
 // the warp that is LAST to finish with a slot refills it at once (no producer role: a producer
 // that also computes paces the whole CTA, see the kernel).  Per block of B output
 // channels a thread
@@ -38,9 +38,9 @@ namespace scb {
 int check_cube_args(const float *cube, int64_t nchan, int64_t ny, int64_t nx, int64_t stride_c, int64_t stride_y);
 int env_int(const char *name, int dflt);
 
-constexpr int SM_TILE = 256;                 // spaxels per CTA = threads (1 KB row bursts)
+constexpr int SM_TILE = 128;                 // spaxels per CTA = threads (512-byte rows; 256 measured 5 % slower, 64 8 % slower)
 constexpr int SM_THREADS = SM_TILE;          // warp 0 also issues the TMA copies
-constexpr int SM_MIN_CTAS = 2;               // register budget: 128 per thread
+constexpr int SM_MIN_CTAS = 4;               // register budget: 128 per thread; four 4-warp rings per SM wait less on their slowest warp than two 8-warp ones
 constexpr int SM_MAX_TAPS = 2 * 16 + 1;
 constexpr int SM_LUT_CHUNKS = (SM_MAX_TAPS + 5) / 6;
 constexpr int SM_B = 16;                     // output channels per block
