@@ -378,10 +378,10 @@ def run_ours(args):
         sa = 8 * voxels / (smooth_ms * 1e-3) / 1e9
         line['spectral_smooth'] = {'ms': smooth_ms, 'voxels_per_s': world * voxels / (smooth_ms * 1e-3),
                                    'roofline': {'bound': 'hbm', 'achieved': sa, 'peak': peak, 'unit': 'GB/s', 'frac': sa / peak,
-                                                'traffic': 17320210000 + 17214935000,
+                                                'traffic': 17322100000 + 17216667000,
                                                 'kernel': 'smooth_tma_kernel<8,INTERVAL,f32> (17 taps)',
                                                 'algorithmic_bytes_per_launch': 8 * voxels,
-                                                'ncu': 'profiles/r01_spectral_smooth_ncu_full_v10.txt'}}
+                                                'ncu': 'profiles/r01_spectral_smooth_ncu_full_v11.txt'}}
     if world == 1 and not args.no_cpu:
         vox, dt, desc = cpu_moments_sample(args.cpu_rows, host_threads())
         line['cpu_baseline'] = {'value': vox / dt, 'unit': 'voxels/s', 'cores': host_threads(), 'kind': 'port',
