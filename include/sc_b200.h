@@ -96,7 +96,7 @@ const char *sc_last_error(void);
 int         sc_version(void);                 /* ABI version, currently 1 */
 /* Scratch a call may need, in bytes; op is one of the SC_OP_* below. */
 enum sc_op { SC_OP_MOMENTS = 1, SC_OP_SPECTRAL_SMOOTH = 2, SC_OP_SPATIAL_SMOOTH = 3,
-             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6, SC_OP_REDUCE = 7 };
+             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6, SC_OP_REDUCE = 7, SC_OP_INGEST = 8 };
 size_t      sc_workspace_bytes(int op, int64_t nchan, int64_t ny, int64_t nx, int64_t aux);
 /* Number of kernel launches this library has enqueued in this process (all streams). */
 int64_t     sc_launch_count(void);
@@ -330,6 +330,15 @@ int sc_reduce_axis0(const float *cube, int64_t nchan, int64_t ny, int64_t nx,
                     double *out_sum, int32_t *out_count, double *out_m2,
                     float *out_min, float *out_max, int32_t *out_argmin, int32_t *out_argmax,
                     void *stream);
+
+/* ---- FITS ingest -------------------------------------------------------
+ * Decodes `n` big-endian FITS samples already on the device (the raw bytes of the data block as
+ * astropy.io.fits maps them, io/fits.py:100-160 `read_data_fits`) to native float32:
+ * out = BZERO + BSCALE * sample, integer samples equal to BLANK become NaN (FITS standard 4.4.2.5).
+ * bitpix is -32, -64, 16, 32 or 8.  The host side streams the file through pinned buffers
+ * (spectral_cube_b200/io_fits.py) and calls this per block. */
+int sc_fits_decode(const void *raw_be, float *out, int64_t n, int bitpix,
+                   double bscale, double bzero, int has_blank, long long blank, void *stream);
 
 /* Celestial pixel->pixel map for two TAN/SIN WCSs (the part of `reproject_interp` that
  * runs through astropy.wcs; FITS WCS papers I/II).  wcs_* = 12 doubles:

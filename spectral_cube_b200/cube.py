@@ -824,6 +824,25 @@ class SpectralCube(BaseSpectralCube):
                                            fill_value=fill_value, header=header,
                                            allow_huge_operations=allow_huge_operations, **kwargs)
 
+    @classmethod
+    def read(cls, filename, format='fits', use_dask=False, **kwargs):
+        """``SpectralCube.read`` for FITS files (io/core.py -> io/fits.py:171-260): the data block is decoded
+        on the device (`sc_fits_decode`), the cube carries ``LazyMask(np.isfinite)`` like the reference's."""
+        if format not in (None, 'fits'):
+            raise NotImplementedError("only FITS cubes can be read (format=%r)" % (format,))
+        from .io_fits import load_fits_cube
+        target = DaskSpectralCube if (use_dask or cls is DaskSpectralCube) else SpectralCube
+        return load_fits_cube(filename, target, **kwargs)
+
+    def write(self, filename, overwrite=False, format='fits'):
+        """io/fits.py:262-282: the cube's (unmasked) data and WCS as a primary-HDU FITS image."""
+        from .io_fits import write_fits
+        hdr = dict(self._header or {})
+        hdr.update(self._wcs.to_header())
+        if self._unit:
+            hdr['BUNIT'] = str(self._unit)
+        write_fits(filename, self._data.cpu().numpy(), hdr, overwrite=overwrite)
+
 
 class DaskSpectralCube(SpectralCube):
     """Mirrors the dask-backed reference class (dask_spectral_cube.py:1376-1650)."""

@@ -67,6 +67,12 @@ class LowerDimensionalObject(np.ndarray):
         hdr['NAXIS'] = self.ndim
         return hdr
 
+    def write(self, filename, format=None, overwrite=False):
+        """lower_dimensional_structures.py:115-124 -> io/fits.py:284-300: the map with its celestial WCS."""
+        from .io_fits import write_fits
+        hdr = dict((k, v) for k, v in self.header.items() if not isinstance(v, (dict, list, tuple)))
+        write_fits(filename, np.asarray(self.value), hdr, overwrite=overwrite)
+
     def to_quantity(self):
         import astropy.units as u          # optional
         return u.Quantity(self.value, u.Unit(self._unit) if isinstance(self._unit, str) else self._unit)

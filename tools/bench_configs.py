@@ -179,6 +179,31 @@ if 'reduce' in which and world == 1:
     del dev, c
     torch.cuda.empty_cache()
 
+if 'ingest' in which and world == 1:
+    # FITS file (page cache) -> pinned staging -> device, decoded on the device
+    import tempfile
+    from spectral_cube_b200 import io_fits
+    nchan, ny, nx = 256, 1024, 2048                       # 2.1 GB of big-endian float32
+    V = nchan * ny * nx
+    host = np.random.default_rng(0).normal(0, 1, (nchan, ny, nx)).astype(np.float32)
+    path = os.path.join(tempfile.gettempdir(), 'sc_b200_ingest.fits')
+    io_fits.write_fits(path, host, dict(benchmark_wcs(nchan, ny, nx).to_header()), overwrite=True)
+    t0 = time.perf_counter(); cube = scb.SpectralCube.read(path); torch.cuda.synchronize(); t1 = time.perf_counter()
+    t0 = time.perf_counter(); cube = scb.SpectralCube.read(path); torch.cuda.synchronize(); t1 = time.perf_counter()
+    ok = bool(torch.equal(cube._data.cpu(), torch.from_numpy(host)))
+    emit('ingest', 'SpectralCube.read of a 2.1 GB FITS cube (page cache -> pinned -> device, decode on device), wall clock', V, (t1 - t0) * 1e3, 4 * V, bit_exact=ok)
+    raw = torch.from_numpy(host.astype('>f4').view(np.uint8).reshape(-1)).cuda()
+    out = torch.empty((nchan, ny, nx), dtype=torch.float32, device='cuda')
+    lib = _lib.load()
+    ms = timeit(lambda: _lib.check(lib.sc_fits_decode(raw.data_ptr(), out.data_ptr(), V, -32, 1.0, 0.0, 0, 0, torch.cuda.current_stream().cuda_stream)))
+    emit('ingest', 'sc_fits_decode alone (device-resident raw bytes -> float32)', V, ms, 8 * V)
+    t0 = time.perf_counter(); ref = np.fromfile(path, dtype='>f4', offset=2880 * 2, count=V).astype(np.float32); t1 = time.perf_counter()
+    if rank == 0:
+        print(json.dumps(dict(config='ingest', what='CPU: numpy fromfile + byte swap of the same file, 1 thread', voxels=V, ms=(t1 - t0) * 1e3)), flush=True)
+    os.unlink(path)
+    del host, cube, raw, out
+    torch.cuda.empty_cache()
+
 if 'target' in which:
     # north-star target: moment0/1/2 + spectral_smooth on the 4096x4096x2048 cube.  One GPU holds the whole
     # 137.4 GB cube (smoothing runs in place); N GPUs hold 1/N of the rows each.
