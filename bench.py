@@ -391,6 +391,48 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config0(args):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: 256x256x128, moment0, no mask.  The CPU
+    leg is the oracle port of `moment_cubewise` (what `moment_auto` picks below 1e8 voxels) on one thread; the
+    GPU leg the same call through the product.  One JSON line."""
+    import warnings
+    import numpy as np
+    import torch
+    import spectral_cube_b200 as scb
+    from spectral_cube_b200.synth import synth_cube, benchmark_wcs
+    from oracle.cube import OracleCube
+    from oracle.wcs import OWCS
+    nchan, ny, nx = 128, 256, 256
+    V = nchan * ny * nx
+    torch.cuda.set_device(0)
+    dev = synth_cube(nchan, ny, nx, nan_permille=0, border=0)
+    c = scb.SpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit='K')
+    for _ in range(5):
+        c._moments_axis0_raw(1)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        c._moments_axis0_raw(1)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    wkw = dict(ctype=['RA---TAN', 'DEC--TAN', 'VRAD'], crval=[24.0, 30.0, -321.214698632], crpix=[nx / 2 + 0.5, ny / 2 + 0.5, 1.0],
+               cdelt=[-5.55555561268e-4, 5.55555561268e-4, 1.28821496879], cunit=['deg', 'deg', 'km/s'])
+    oc = OracleCube(dev.cpu().numpy(), OWCS(**wkw), unit='K', mask=None)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ref = oc.moment(order=0, how='auto')[0]
+    cpu_s = (time.perf_counter() - t0) / 5
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ok = bool(np.allclose(c.moment0().value, ref, rtol=1e-5, equal_nan=True))
+    print(json.dumps({'metric': 'voxels/sec', 'value': V / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': 1, 'steps': args.steps,
+                      'ms_per_step': ms, 'config': {'workload': 'configs[0]: 256x256x128 float32 synthetic cube, moment0, no mask (33.6 MB: L2 resident)'},
+                      'parity_rtol_1e5': ok,
+                      'cpu_baseline': {'value': V / cpu_s, 'unit': 'voxels/s', 'cores': 1, 'kind': 'port',
+                                       'sample': 'the whole cube, oracle moment_cubewise, 1 thread'}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -402,8 +444,11 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-smooth', action='store_true')
+    ap.add_argument('--config0', action='store_true', help="BASELINE configs[0] (the reference's CPU-runnable case) instead of configs[1]")
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.config0:
+        run_config0(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

@@ -64,22 +64,8 @@ if 'c1' in which and world == 1:
     ms = timeit(lambda: c._moments_axis0_raw(1), n=50, warm=5)
     V = nchan * ny * nx
     emit('c1', 'moment0, no mask, 256x256x128 (33.6 MB: L2 resident)', V, ms, 4 * V + 8 * ny * nx)
-    # CPU: the reference's own CPU-runnable case, cube strategy (moment_auto picks it below 1e8 voxels)
-    from oracle.cube import OracleCube
-    from oracle.wcs import OWCS
-    host = dev.cpu().numpy()
-    wkw = dict(ctype=['RA---TAN', 'DEC--TAN', 'VRAD'], crval=[24.0, 30.0, -321.214698632], crpix=[nx / 2 + 0.5, ny / 2 + 0.5, 1.0],
-               cdelt=[-5.55555561268e-4, 5.55555561268e-4, 1.28821496879], cunit=['deg', 'deg', 'km/s'])
-    oc = OracleCube(host, OWCS(**wkw), unit='K', mask=None)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        ref = oc.moment(order=0, how='auto')[0]
-    cpu_s = (time.perf_counter() - t0) / 5
-    got = c.moment0().value
-    ok = bool(np.allclose(got, ref, rtol=1e-5, equal_nan=True))
-    if rank == 0:
-        print(json.dumps(dict(config='c1', what='CPU oracle moment0 (cube strategy), 1 thread', voxels=V, ms=cpu_s * 1e3,
-                              voxels_per_s=V / cpu_s, parity_rtol_1e5=ok)), flush=True)
+    # (the CPU leg of this config -- the oracle, cube strategy, one thread -- is `python bench.py --config0`: only
+    #  bench.py, the tests and smoke() may execute oracle/)
     del dev, c
 
 if 'c3' in which and world == 1:
