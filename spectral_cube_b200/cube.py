@@ -314,6 +314,47 @@ class BaseSpectralCube(object):
             self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         return self._workspace
 
+    # -- views (spectral_cube.py:1290-1380 `__getitem__`, :1822-1876 `spectral_slab`) --------------------
+    def __getitem__(self, view):
+        """Sub-cube for a view made of slices (a VIEW of the same device memory, like the reference's);
+        the WCS follows `wcs_utils.slice_wcs`, the mask is sliced alongside.  Integer indices (which give
+        spectra and slices in the reference) are not part of the device path."""
+        from .masks import _slice3
+        view = _slice3(view)
+        if any(v.step is not None and v.step < 1 for v in view):
+            raise NotImplementedError("negative steps are not supported")
+        data = self._data[view]
+        if 0 in data.shape:
+            raise ValueError("the view selects no voxel")
+        wcs = self._wcs.copy()
+        for np_axis, sl in enumerate(view):
+            w = 2 - np_axis                                       # numpy axis -> FITS axis index
+            start, stop, step = sl.indices(self.shape[np_axis])
+            # wcs_utils.slice_wcs: crpix follows the first kept pixel; a step stretches cdelt about its centre
+            wcs.crpix[w] = (wcs.crpix[w] - start - 0.5) / step + 0.5
+            wcs.cdelt[w] = wcs.cdelt[w] * step
+        mask = self._mask[view] if self._mask is not None else None
+        cube = self._new_cube_with(data=data, wcs=wcs, mask=mask)
+        if self._mask is None:
+            cube._mask = None
+        return cube
+
+    def closest_spectral_channel(self, value):
+        """spectral_cube.py:1800-1820 (value in the cube's spectral unit)."""
+        value = float(getattr(value, 'value', value))
+        return int(np.argmin(np.abs(np.asarray(self.spectral_axis, dtype=np.float64) - value)))
+
+    def spectral_slab(self, lo, hi):
+        """Extract a new cube between two spectral coordinates (spectral_cube.py:1822-1876): a view."""
+        ilo, ihi = self.closest_spectral_channel(lo), self.closest_spectral_channel(hi)
+        if ilo == ihi:
+            warnings.warn("The maxmimum and minimum spectral channel in the spectral"
+                          "slab are identical; this indicates that one or both are "
+                          "likely incorrect and/or out of range.", SpectralCubeWarning)
+        if ilo > ihi:
+            ilo, ihi = ihi, ilo
+        return self[ilo:ihi + 1, :, :]
+
     # -- smoothing (spectral_cube.py:3186-3222, 2808-2842; dask_spectral_cube.py:880-917, 962-993) ----
     @staticmethod
     def _kernel_array(kernel, ndim):

@@ -167,6 +167,23 @@ class MaskBase(object):
                 raise ValueError("data shape cannot be broadcast to match mask shape")
 
 
+def _slice3(view):
+    """Normalise a cube view to three slices (masks.py `__getitem__` / wcs_utils.slice_wcs take the same)."""
+    if not isinstance(view, tuple):
+        view = (view,)
+    if any(v is Ellipsis for v in view) or len(view) > 3 or not all(isinstance(v, slice) for v in view):
+        raise NotImplementedError("only views made of up to three slices are supported")
+    return tuple(view) + (slice(None),) * (3 - len(view))
+
+
+def _slice_broadcast(t, view):
+    """Slice a tensor that is broadcastable to the cube: axes of length 1 stay as they are."""
+    view = _slice3(view)
+    if t.dim() < 3:
+        view = view[3 - t.dim():]
+    return t[tuple(slice(None) if t.shape[i] == 1 else v for i, v in enumerate(view))]
+
+
 class InvertedMask(MaskBase):
     """masks.py:337-361"""
 
@@ -179,6 +196,9 @@ class InvertedMask(MaskBase):
 
     def _reference_tensor(self):
         return self._mask._reference_tensor()
+
+    def __getitem__(self, view):
+        return InvertedMask(self._mask[view])
 
     def _lower(self, low):
         a = self._mask._lower(low)
@@ -213,6 +233,9 @@ class CompositeMask(MaskBase):
     def _reference_tensor(self):
         r = self._mask1._reference_tensor()
         return r if r is not None else self._mask2._reference_tensor()
+
+    def __getitem__(self, view):
+        return CompositeMask(self._mask1[view], self._mask2[view], operation=self._operation)
 
     def _lower(self, low):
         a = self._mask1._lower(low)
@@ -249,6 +272,15 @@ class BooleanArrayMask(MaskBase):
         torch = _torch()
         return torch.zeros(self._shape, dtype=torch.float32, device='cuda')
 
+    def __getitem__(self, view):
+        """masks.py:559-566: the sliced array (a view of the same device memory)."""
+        sub = _slice_broadcast(self._mask, view)
+        new = BooleanArrayMask.__new__(BooleanArrayMask)
+        new._mask, new._mask_type, new._wcs = sub, self._mask_type, self._wcs
+        full = _torch().empty(self._shape, dtype=_torch().uint8, device='meta')[_slice3(view)]
+        new._shape = tuple(full.shape)
+        return new
+
     def _lower(self, low):
         i = low.add(kind=_lib.MASK_BOOL, array_dtype=_lib.U8, **low.array_fields(self._mask))
         if self._mask_type == 'exclude':
@@ -277,6 +309,10 @@ class LazyMask(MaskBase):
 
     def _reference_tensor(self):
         return self._data
+
+    def __getitem__(self, view):
+        """masks.py:641-647: the same function on the sliced data (a view: no copy)."""
+        return LazyMask(self._function, data=self._data[_slice3(view)], wcs=self._wcs)
 
     def _lower(self, low):
         if self._function is np.isfinite:
@@ -321,6 +357,15 @@ class LazyComparisonMask(LazyMask):
         self._function = function
         self._comparison_value = comparison_value
 
+    def __getitem__(self, view):
+        """masks.py:735-745: sliced data; an array to compare with is sliced alongside (broadcast axes stay)."""
+        cv = self._comparison_value
+        if hasattr(cv, 'shape') and len(cv.shape) > 0:
+            torch = _torch()
+            t = cv if isinstance(cv, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cv, dtype=np.float64))
+            cv = _slice_broadcast(t, view)
+        return LazyComparisonMask(self._function, cv, data=self._data[_slice3(view)], wcs=self._wcs)
+
     def _lower(self, low):
         cv = self._comparison_value
         if hasattr(cv, 'shape') and len(cv.shape) > 0:
@@ -342,6 +387,9 @@ class LazyComparisonMask(LazyMask):
 class FunctionMask(MaskBase):
     """masks.py:760-803: ``function(data, wcs, view)`` -> boolean array; evaluated on the cube
     the mask is applied to.  The function must work on a torch device tensor."""
+
+    def __getitem__(self, view):
+        return self                                              # evaluated on whatever data it is applied to
 
     def __init__(self, function):
         self._function = function

@@ -129,3 +129,19 @@ def test_moment_map_written_and_read_back(tmp_path):
     assert np.array_equal(np.isnan(back), np.isnan(m0.value))
     ok = ~np.isnan(back)
     assert np.array_equal(back[ok], m0.value[ok])
+
+
+@pytest.mark.gpu
+def test_degenerate_stokes_axis_is_dropped(tmp_path):
+    """A 4-axis file with NAXIS4 = 1 (the layout of the reference's example_cube.fits): one Stokes plane."""
+    import spectral_cube_b200 as scb
+    path = str(tmp_path / 's.fits')
+    d = _cube((1, 4, 7, 9), seed=2)
+    io_fits.write_fits(path, d, dict(HDR, CTYPE4='STOKES', CRVAL4=1.0, CRPIX4=1.0, CDELT4=1.0))
+    cube = scb.SpectralCube.read(path)
+    assert cube.shape == (4, 7, 9)
+    assert np.array_equal(cube._data.cpu().numpy().view(np.uint32), d[0].view(np.uint32))
+    d2 = np.zeros((2, 3, 4), dtype=np.float32)
+    io_fits.write_fits(str(tmp_path / 'img.fits'), d2[0], HDR)
+    with pytest.raises(io_fits.FITSReadError):
+        scb.SpectralCube.read(str(tmp_path / 'img.fits'))               # "Data should be 3- or 4-dimensional"

@@ -111,3 +111,39 @@ def test_peak_and_noise_maps_at_scale():
     assert torch.equal(r2['sum'][ok], 2 * r['sum'][ok])
     assert torch.allclose(r2['m2'][ok], 4 * r['m2'][ok], rtol=1e-12)
     assert torch.isnan(r['sum'][~ok]).all() and torch.isnan(r['max'][~ok]).all()
+
+
+def test_reductions_without_a_mask_and_with_infinities():
+    """`mask=None` (a cube built straight from an array, spectral_cube/tests/test_spectral_cube.py:2686-2700):
+    NaNs are skipped like the nan-functions do, infinities take part."""
+    import spectral_cube_b200 as scb
+    rng = np.random.default_rng(21)
+    data = rng.normal(0, 1, (20, 6, 8)).astype(np.float32)
+    data[3, 1, 1] = np.nan
+    data[5, 2, 2] = np.inf
+    data[7, 3, 3] = -np.inf
+    data[:, 4, 4] = np.nan
+    sc = scb.SpectralCube(data, scb.CubeWCS(**BENCH_WCS), unit='K')            # mask is None
+    oc = oracle_cube(data, BENCH_WCS, mask=None)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.testing.assert_array_equal(sc.max(axis=0).value, oc.max(axis=0))
+        np.testing.assert_array_equal(sc.min(axis=0).value, oc.min(axis=0))
+        got, want = sc.sum(axis=0).value, oc.sum(axis=0)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    assert got[2, 2] == np.inf and got[3, 3] == -np.inf
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=1e-5, atol=1e-5)
+    assert sc.argmax(axis=0)[2, 2] == 5 and sc.argmin(axis=0)[3, 3] == 7
+
+
+def test_reductions_on_views_with_odd_widths():
+    """A spatial sub-cube view (row stride != nx, odd width): the scalar-load path."""
+    data = _random_cube((24, 12, 21), seed=8)
+    sc, oc = gpu_cube(data, BENCH_WCS), oracle_cube(data, BENCH_WCS)
+    sub = sc[:, 2:11, 3:20]
+    osub = oracle_cube(data[:, 2:11, 3:20], BENCH_WCS)
+    np.testing.assert_array_equal(sub.max(axis=0).value, osub.max(axis=0))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        assert_maps_close(sub.mean(axis=0).value, osub.mean(axis=0), rtol=1e-5, atol=1e-6)
