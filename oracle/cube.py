@@ -195,6 +195,9 @@ class OracleCube(object):
             return function(self._get_filled_data(fill=fill), axis=axis)
 
     def sum(self, axis=None):
+        if axis is None:                                                               # np_compat.allbadtonan, whole cube
+            filled = self._get_filled_data(fill=np.nan)
+            return np.float32(np.nan) if np.isnan(filled).all() else np.nansum(filled)
         return self._apply_numpy_function(_mom.nansum_allbad_nan, axis=axis)            # :578-588 (np_compat.allbadtonan)
 
     def mean(self, axis=None):

@@ -52,6 +52,51 @@ def _stream():
     return _torch().cuda.current_stream().cuda_stream
 
 
+# ---- whole-cube statistics from the per-spaxel partials of one device pass (device-agnostic torch code:
+#      tests/test_reduce_host.py runs it on CPU tensors) ------------------------------------------------------
+def whole_sum(torch, sum_map, count_map):
+    return float(torch.nansum(sum_map).item()) if int(count_map.sum().item()) > 0 else float('nan')
+
+
+def whole_mean(torch, sum_map, count_map):
+    n = int(count_map.sum().item())
+    return float(torch.nansum(sum_map).item()) / n if n > 0 else float('nan')
+
+
+def whole_std(torch, sum_map, count_map, m2_map, ddof=0):
+    """Chan et al. combination: M2 = sum m2_i + sum n_i (mean_i - mean)^2."""
+    n_i = count_map.to(torch.float64)
+    n = float(n_i.sum().item())
+    if n - ddof <= 0:
+        return float('nan')
+    ok = n_i > 0
+    s_i = torch.where(ok, sum_map, torch.zeros_like(sum_map))
+    mean = float(s_i.sum().item()) / n
+    mean_i = s_i / torch.clamp(n_i, min=1.0)
+    m2 = torch.where(ok, m2_map + n_i * (mean_i - mean) ** 2, torch.zeros_like(n_i)).sum().item()
+    return float(np.sqrt(m2 / (n - ddof)))
+
+
+def whole_extremum(torch, ext_map, which):
+    ok = ~torch.isnan(ext_map)
+    if not bool(ok.any()):
+        return float('nan')
+    return float((ext_map[ok].max() if which == 'max' else ext_map[ok].min()).item())
+
+
+def whole_arg_extremum(torch, ext_map, idx_map, which):
+    """Flat C-order index of the FIRST extremum like np.nanarg*: the smallest (channel, spaxel) among the ties;
+    0 ("arbitrary" in the reference) when nothing takes part."""
+    ok = ~torch.isnan(ext_map)
+    if not bool(ok.any()):
+        return 0
+    best = ext_map[ok].max() if which == 'max' else ext_map[ok].min()
+    ny, nx = ext_map.shape
+    spaxel = torch.arange(ny * nx, device=ext_map.device, dtype=torch.int64).view(ny, nx)
+    flat = idx_map.to(torch.int64) * (ny * nx) + spaxel
+    return int(flat[ok & (ext_map == best)].min().item())
+
+
 class BaseSpectralCube(object):
     _mirrors_dask = False
 
@@ -618,9 +663,9 @@ class BaseSpectralCube(object):
         return outs
 
     def _reduction_axis(self, axis, name):
-        if axis != 0:
-            raise NotImplementedError("%s(axis=%r): only reductions along the spectral axis (axis=0) run on the "
-                                      "device; see SURVEY.md 8(f)" % (name, axis))
+        if axis not in (0, None):
+            raise NotImplementedError("%s(axis=%r): only reductions along the spectral axis (axis=0) and over the "
+                                      "whole cube (axis=None) run on the device; see SURVEY.md 8(f)" % (name, axis))
 
     def _collapsed(self, values, unit):
         """Projection of a collapsed spectral axis (spectral_cube.py:395-414)."""
@@ -631,43 +676,63 @@ class BaseSpectralCube(object):
     def _np_dtype(self):
         return np.float32          # the cube's dtype: the nan-functions of the reference keep it
 
+    # axis=None: the per-spaxel partials of the one device pass are combined on the (ny, nx) maps -- S values
+    # against the V voxels of the pass.  Scalars come back as numpy float32 (the reference wraps them in a Quantity).
     def sum(self, axis=None, how='auto', **kwargs):
-        """Sum over the spectral axis; spaxels with nothing included are NaN (np_compat.allbadtonan)."""
+        """Sum over the spectral axis (or everything); nothing included -> NaN (np_compat.allbadtonan)."""
         self._reduction_axis(axis, 'sum')
-        r = self._reduce_axis0_raw({'sum'})
+        r = self._reduce_axis0_raw({'sum', 'count'} if axis is None else {'sum'})
+        if axis is None:
+            return self._np_dtype()(whole_sum(_torch(), r['sum'], r['count']))
         return self._collapsed(r['sum'].cpu().numpy().astype(self._np_dtype()), self._unit)
 
     def mean(self, axis=None, how='cube', **kwargs):
         self._reduction_axis(axis, 'mean')
-        r = self._reduce_axis0_raw({'sum', 'count'})
         torch = _torch()
+        r = self._reduce_axis0_raw({'sum', 'count'})
+        if axis is None:
+            return self._np_dtype()(whole_mean(torch, r['sum'], r['count']))
         out = r['sum'] / r['count'].to(torch.float64)            # 0 / 0 never happens: sum is NaN there
         return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
 
     def std(self, axis=None, how='cube', ddof=0, **kwargs):
         self._reduction_axis(axis, 'std')
-        r = self._reduce_axis0_raw({'m2', 'count'})
         torch = _torch()
+        if axis is None:
+            r = self._reduce_axis0_raw({'sum', 'count', 'm2'})
+            return self._np_dtype()(whole_std(torch, r['sum'], r['count'], r['m2'], ddof))
+        r = self._reduce_axis0_raw({'m2', 'count'})
         n = r['count'].to(torch.float64) - float(ddof)
         out = torch.sqrt(r['m2'] / torch.where(n > 0, n, torch.full_like(n, float('nan'))))
         return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
 
     def max(self, axis=None, how='auto', **kwargs):
         self._reduction_axis(axis, 'max')
-        return self._collapsed(self._reduce_axis0_raw({'max'})['max'].cpu().numpy(), self._unit)
+        m = self._reduce_axis0_raw({'max'})['max']
+        if axis is None:
+            return self._np_dtype()(whole_extremum(_torch(), m, 'max'))
+        return self._collapsed(m.cpu().numpy(), self._unit)
 
     def min(self, axis=None, how='auto', **kwargs):
         self._reduction_axis(axis, 'min')
-        return self._collapsed(self._reduce_axis0_raw({'min'})['min'].cpu().numpy(), self._unit)
+        m = self._reduce_axis0_raw({'min'})['min']
+        if axis is None:
+            return self._np_dtype()(whole_extremum(_torch(), m, 'min'))
+        return self._collapsed(m.cpu().numpy(), self._unit)
+
+    def _arg_extremum(self, axis, which):
+        self._reduction_axis(axis, 'arg' + which)
+        r = self._reduce_axis0_raw({which, 'arg' + which})
+        if axis is not None:
+            return r['arg' + which].cpu().numpy().astype(np.int64)
+        return whole_arg_extremum(_torch(), r[which], r['arg' + which], which)
 
     def argmax(self, axis=None, how='auto', **kwargs):
         """Channel of the (first) maximum; arbitrary (0) where nothing is included (spectral_cube.py:800-811)."""
-        self._reduction_axis(axis, 'argmax')
-        return self._reduce_axis0_raw({'argmax'})['argmax'].cpu().numpy().astype(np.int64)
+        return self._arg_extremum(axis, 'max')
 
     def argmin(self, axis=None, how='auto', **kwargs):
-        self._reduction_axis(axis, 'argmin')
-        return self._reduce_axis0_raw({'argmin'})['argmin'].cpu().numpy().astype(np.int64)
+        return self._arg_extremum(axis, 'min')
 
     # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
     def _moments_axis0_raw(self, want_bits):

@@ -102,6 +102,28 @@ def test_first_occurrence_and_ties():
     assert (sc.max(axis=0).value == 5.0).all() and (sc.min(axis=0).value == -3.0).all()
 
 
+@pytest.mark.parametrize('maskname', ['isfinite', 'gt3', 'or'])
+def test_whole_cube_reductions(maskname):
+    """axis=None (the default of the reference's `sum/mean/std/max/min/argmax/argmin`)."""
+    data, sc, oc = _pair((33, 7, 13), maskname, 'whole')
+    # the reference applies the nan-function to the filled cube (spectral_cube.py:446-454); float64 here so that
+    # the comparison is not limited by numpy's float32 accumulation
+    filled = oc._get_filled_data(fill=np.nan).astype(np.float64)
+    for name, fn in (('sum', np.nansum), ('mean', np.nanmean), ('std', np.nanstd), ('max', np.nanmax), ('min', np.nanmin)):
+        got, want = getattr(sc, name)(), fn(filled)
+        assert np.isclose(float(got), float(want), rtol=1e-6, atol=1e-6), (name, got, want)
+        assert np.isclose(float(getattr(oc, name)()), float(want), rtol=1e-3, atol=1e-3), name     # the oracle method agrees
+    assert np.isclose(float(sc.std(ddof=1)), float(np.nanstd(filled, ddof=1)), rtol=1e-6)
+    inc = oc._mask_include() & ~np.isnan(data)
+    assert sc.argmax() == int(np.argmax(np.where(inc, data, -np.inf)))
+    assert sc.argmin() == int(np.argmin(np.where(inc, data, np.inf)))
+    tie = np.zeros((5, 3, 4), dtype=np.float32)
+    tie[2, 1, 1] = tie[1, 2, 3] = tie[1, 0, 2] = 9.0
+    assert gpu_cube(tie, BENCH_WCS).argmax() == int(np.argmax(tie))            # first in C order among ties
+    blank = gpu_cube(np.full((4, 3, 4), np.nan, dtype=np.float32), BENCH_WCS)
+    assert np.isnan(blank.sum()) and np.isnan(blank.max()) and np.isnan(blank.std()) and blank.argmax() == 0
+
+
 def test_only_the_spectral_axis_runs_on_the_device():
     sc = gpu_cube(np.ones((4, 4, 4), dtype=np.float32), BENCH_WCS)
     with pytest.raises(NotImplementedError):
