@@ -96,7 +96,7 @@ const char *sc_last_error(void);
 int         sc_version(void);                 /* ABI version, currently 1 */
 /* Scratch a call may need, in bytes; op is one of the SC_OP_* below. */
 enum sc_op { SC_OP_MOMENTS = 1, SC_OP_SPECTRAL_SMOOTH = 2, SC_OP_SPATIAL_SMOOTH = 3,
-             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6, SC_OP_REDUCE = 7, SC_OP_INGEST = 8 };
+             SC_OP_SPECTRAL_INTERP = 4, SC_OP_REPROJECT = 5, SC_OP_SMOOTH_MOMENTS = 6, SC_OP_REDUCE = 7, SC_OP_INGEST = 8, SC_OP_POINTWISE = 9 };
 size_t      sc_workspace_bytes(int op, int64_t nchan, int64_t ny, int64_t nx, int64_t aux);
 /* Number of kernel launches this library has enqueued in this process (all streams). */
 int64_t     sc_launch_count(void);
@@ -256,6 +256,17 @@ int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
                          const float *halo_top, const float *halo_bot, int halo_rows,
                          int plane_passthrough,
                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* In-place epilogue of `convolve_to` over a (nchan, ny, nx) float32/float64 block (x stride 1), one pass:
+ * `data *= factor` -- the Jy/beam rescale by target.sr / beam.sr of each convolved channel image
+ * (spectral_cube.py:3369-3378; VaryingResolutionSpectralCube :4207-4233); with `nan_to_zero`, NaN -> 0.0 --
+ * what `astropy.convolution.convolve_fft` (the numpy class's default there) returns for output pixels whose
+ * kernel window holds no valid input, where the direct `convolve` keeps the NaN; otherwise NaN stays NaN.
+ * `skip_planes` (device uint8[nchan] or NULL): channels with a non-zero flag are left untouched (planes that
+ * `_apply_spatial_function` copies through, spectral_cube.py:161-172). */
+int sc_scale(void *data, int dtype, int64_t nchan, int64_t ny, int64_t nx,
+             int64_t stride_c, int64_t stride_y, double factor, int nan_to_zero,
+             const uint8_t *skip_planes, void *stream);
 
 /* Write the FILLED edge rows a neighbour needs: rows [row0, row0+nrows) of every channel,
  * mask applied (excluded -> fill), into a contiguous (nchan, nrows, nx) float32 buffer. */

@@ -48,7 +48,11 @@ class BeamUnitsError(Exception):
 
 class OracleCube(object):
     def __init__(self, data, wcs, mask='isfinite', unit='K', fill_value=np.nan,
-                 spectral_unit=None, use_dask=False, meta=None):
+                 spectral_unit=None, use_dask=False, meta=None, beam=None, beams=None, goodbeams_mask=None):
+        # `beam`: one OBeam (SpectralCube); `beams`: one per channel (VaryingResolutionSpectralCube)
+        self.beam, self.beams = beam, beams
+        self.goodbeams_mask = (np.array([b.isfinite for b in beams]) if beams is not None and goodbeams_mask is None
+                               else goodbeams_mask)
         self._data = data
         self._wcs = wcs
         # io/fits.py:214 attaches LazyMask(np.isfinite) on read; direct construction may pass None
@@ -83,7 +87,8 @@ class OracleCube(object):
     def _new_cube_with(self, **kw):
         args = dict(data=self._data, wcs=self._wcs, mask=self._mask, unit=self.unit,
                     fill_value=self._fill_value, spectral_unit=self._spectral_unit,
-                    use_dask=self.use_dask, meta=self.meta)
+                    use_dask=self.use_dask, meta=self.meta, beam=self.beam, beams=self.beams,
+                    goodbeams_mask=self.goodbeams_mask)
         args.update(kw)
         return OracleCube(**args)
 
@@ -299,6 +304,57 @@ class OracleCube(object):
                 else:
                     out[c] = img                                 # :169-172
         return self._new_cube_with(data=out)
+
+    # -- convolution to a common beam -----------------------------------------------------------
+    def _pixscale(self):
+        """proj_plane_pixel_area(wcs.celestial)**0.5 in degrees (spectral_cube.py:3369)."""
+        m = np.asarray(self._wcs.pixel_scale_matrix)[:2, :2]
+        return float(np.sqrt(abs(np.linalg.det(m))))
+
+    def mask_channels(self, goodchannels):
+        goodchannels = np.asarray(goodchannels, dtype=bool)                  # :4289-4300
+        cube = self.with_mask(np.broadcast_to(goodchannels[:, None, None], self.shape).copy())
+        if self.beams is not None:
+            cube.goodbeams_mask = np.logical_and(goodchannels, self.goodbeams_mask)
+        return cube
+
+    def convolve_to(self, beam, allow_smaller=False, convolve=None):
+        """spectral_cube.py:3335-3392 (one beam; per image through ``_apply_spatial_function``) and :4127-4240
+        (per-channel beams); dask_spectral_cube.py:1412-1464, 1512-1630.  ``convolve`` defaults to the class's
+        default: ``convolve_fft`` for the numpy classes, ``convolve`` for the dask ones."""
+        if convolve is None:
+            convolve = _conv.convolve if self.use_dask else _conv.convolve_fft
+        jybeam = self.unit.replace(' ', '').lower() == 'jy/beam'
+        pixscale = self._pixscale()
+        data = self.unitless_filled_data
+        if self.beams is None:
+            if beam == self.beam:
+                warnings.warn("The given beam is identical to the current beam. Skipping convolution.")
+                return self
+            kernel = beam.deconvolve(self.beam).as_kernel(pixscale)
+            factor = beam.sr / self.beam.sr if jybeam else 1.
+            out = np.empty(self.shape, dtype=data.dtype if self.use_dask else float)
+            for c in range(self.shape[0]):
+                if self.use_dask or np.any(self._mask_include((c, slice(None), slice(None)))):
+                    out[c] = convolve(data[c], kernel, normalize_kernel=True) * factor
+                else:
+                    out[c] = data[c]                                          # :169-172
+            return self._new_cube_with(data=out, beam=beam)
+        plan = []
+        for bm, valid in zip(self.beams, self.goodbeams_mask):
+            if not valid or beam == bm:
+                plan.append((None, 1.))
+                continue
+            try:
+                plan.append((beam.deconvolve(bm).as_kernel(pixscale), beam.sr / bm.sr if jybeam else 1.))
+            except ValueError:
+                if not allow_smaller:
+                    raise
+                plan.append((None, 1.))
+        out = np.empty(self.shape, dtype=data.dtype if self.use_dask else float)
+        for c, (kernel, factor) in enumerate(plan):
+            out[c] = data[c] if kernel is None else convolve(data[c], kernel, normalize_kernel=True) * factor
+        return self._new_cube_with(data=out, beam=beam, beams=None, goodbeams_mask=None)
 
     # -- resampling ----------------------------------------------------------------------------
     def spectral_interpolate(self, spectral_grid, suppress_smooth_warning=False, fill_value=None):

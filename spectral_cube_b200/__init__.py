@@ -7,7 +7,10 @@ Everything numerical runs in hand-written CUDA (sm_100a) from ``csrc/`` through 
 ``include/sc_b200.h``; there is no CPU fallback.
 """
 from .cube import (SpectralCube, DaskSpectralCube, BaseSpectralCube, VarianceWarning,
-                   SmoothingWarning, BeamUnitsError, SpectralCubeWarning, SIGMA2FWHM)
+                   SmoothingWarning, BeamUnitsError, SpectralCubeWarning, SIGMA2FWHM,
+                   VaryingResolutionSpectralCube, DaskVaryingResolutionSpectralCube, BeamWarning,
+                   NonFiniteBeamsWarning)
+from .beam import Beam, Beams, BeamError, NoBeamError, EllipticalGaussian2DKernel
 from .masks import (MaskBase, InvertedMask, CompositeMask, BooleanArrayMask, LazyMask,
                     LazyComparisonMask, FunctionMask)
 from .projection import Projection
@@ -20,4 +23,6 @@ __all__ = ['SpectralCube', 'DaskSpectralCube', 'BaseSpectralCube', 'Projection',
            'LazyComparisonMask', 'FunctionMask', 'VarianceWarning', 'SmoothingWarning',
            'BeamUnitsError', 'SpectralCubeWarning', 'SIGMA2FWHM',
            'Kernel1D', 'Kernel2D', 'Gaussian1DKernel', 'Gaussian2DKernel', 'Tophat2DKernel',
-           'Box1DKernel', 'CustomKernel']
+           'Box1DKernel', 'CustomKernel', 'VaryingResolutionSpectralCube',
+           'DaskVaryingResolutionSpectralCube', 'Beam', 'Beams', 'BeamError', 'NoBeamError', 'BeamWarning',
+           'NonFiniteBeamsWarning', 'EllipticalGaussian2DKernel']

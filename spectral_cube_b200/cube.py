@@ -19,6 +19,7 @@ from . import masks as _masks
 from .masks import (BooleanArrayMask, LazyMask, LazyComparisonMask, MaskBase, lower_mask)
 from .projection import Projection, _unit_mul, _unit_pow
 from .wcs import as_cube_wcs, spectral_unit_scale
+from .beam import Beam, Beams, BeamError, NoBeamError
 
 SIGMA2FWHM = 2. * np.sqrt(2. * np.log(2.))        # spectral_cube.py:82
 MEMORY_THRESHOLD = 1e8                            # cube_utils.py:266-268
@@ -136,6 +137,8 @@ class BaseSpectralCube(object):
         self._spectral_unit = spectral_unit if spectral_unit is not None else self._wcs.cunit[2]
         self._spectral_scale = spectral_unit_scale(self._wcs.cunit[2], self._spectral_unit)
         self._workspace = None
+        self._beam = None
+        self._passthrough_flags = None
 
     @property
     def _data_hi(self):
@@ -182,6 +185,14 @@ class BaseSpectralCube(object):
             spectral_unit=self._spectral_unit if spectral_unit is None else spectral_unit)
         if still_lazy:
             cube._data_t, cube._pending = None, self._pending
+        beam = kw.get('beam', None)
+        if beam is None:
+            beam = getattr(self, '_beam', None)               # spectral_cube.py:3733-3738
+        cube._beam = None
+        if beam is not None and hasattr(cube, '_attach_beam'):
+            cube._meta = dict(cube._meta)
+            cube._header = dict(cube._header)
+            cube._attach_beam(beam)
         return cube
 
     # -- basic properties ------------------------------------------------------------------------
@@ -483,20 +494,28 @@ class BaseSpectralCube(object):
                                                  counts.data_ptr(), _stream()))
         return counts
 
-    def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0, strategy_counts=None):
+    def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0, strategy_counts=None,
+                            out=None, passthrough=None):
+        """`out` may be a (nchan, ny, nx) view of a larger tensor (x stride 1): `convolve_to` on per-channel
+        beams writes each channel plane of one result cube with its own kernel."""
         torch = _torch()
         lib = _lib.load()
         src = self._data
         nchan, ny, nx = self.shape
-        out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
-                          device=src.device)
+        if out is None:
+            out = torch.empty((nchan, ny, nx), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
+                              device=src.device)
         desc, keep = self._mask_desc()
         ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPATIAL_SMOOTH, nchan, ny, nx, k2d.size))
         ht = halo_top.data_ptr() if halo_top is not None else None
         hb = halo_bot.data_ptr() if halo_bot is not None else None
         common = (src.data_ptr(), out.data_ptr(), out_dtype, nchan, ny, nx, src.stride(0), src.stride(1),
                   out.stride(0), out.stride(1), desc, float(self._fill_value))
-        passthrough = 0 if self._mirrors_dask else 1     # _apply_spatial_function (:161-172)
+        if passthrough is None:
+            passthrough = 0 if self._mirrors_dask else 1     # _apply_spatial_function (:161-172)
+        # the library leaves the per-channel "copied through" flags in the workspace behind the taps
+        self._passthrough_flags = (ws[k2d.size * 8 + 512: k2d.size * 8 + 512 + nchan]
+                                   if passthrough and desc.n_nodes > 0 else None)
         sep = self._separable_factors(k2d)
         if sep is not None:
             (ya, yp), (xa, xp) = _lib.as_double_array(sep[0]), _lib.as_double_array(sep[1])
@@ -516,6 +535,103 @@ class BaseSpectralCube(object):
         if self._mirrors_dask:
             return self._new_cube_with(data=self._run_spatial_smooth(k2d, _lib.F32))
         return self._new_cube_reporting_f64(self._run_spatial_smooth(k2d, _lib.F32))
+
+    # -- convolution to a common beam (spectral_cube.py:3335-3392; dask_spectral_cube.py:1412-1464) ------
+    @property
+    def beam(self):
+        """base_class.py:830-838"""
+        if getattr(self, '_beam', None) is None:
+            raise NoBeamError("No beam is defined for this SpectralCube or the"
+                              " beam information could not be parsed from the"
+                              " header. A `~radio_beam.Beam` object can be"
+                              " added using `cube.with_beam`.")
+        return self._beam
+
+    @beam.setter
+    def beam(self, obj):
+        self._beam = None if obj is None else Beam.coerce(obj)
+
+    def with_beam(self, beam, raise_error_jybm=True):
+        """Attach a beam object (spectral_cube.py:3741-3765)."""
+        beam = Beam.coerce(beam)
+        self.check_jybeam_smoothing(raise_error_jybm=raise_error_jybm)
+        return self._new_cube_with(beam=beam)
+
+    def _attach_beam(self, beam):
+        self._beam = beam
+        if beam is not None:
+            self._meta['beam'] = beam
+            self._header.update(beam.to_header_keywords())
+
+    def _is_jybeam(self):
+        return str(self._unit).replace(' ', '').lower() == 'jy/beam'
+
+    def _pixscale_deg(self):
+        """``proj_plane_pixel_area(self.wcs.celestial)**0.5`` in degrees (:3369)."""
+        m = self._wcs.pixel_scale_matrix[:2, :2]
+        return float(np.sqrt(abs(m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0])))
+
+    @staticmethod
+    def _check_convolve_kwargs(kwargs):
+        """The device convolution implements astropy's defaults (zero-filled boundary, NaNs interpolated, kernel
+        normalised), under which ``convolve`` and ``convolve_fft`` agree; anything else is refused, not ignored."""
+        supported = {'nan_treatment': 'interpolate', 'boundary': 'fill', 'fill_value': 0.0, 'preserve_nan': False,
+                     'normalize_kernel': True}
+        for key, val in kwargs.items():
+            if key in supported:
+                if val != supported[key]:
+                    raise NotImplementedError("convolution keyword %s=%r is not available on the device path "
+                                              "(only %r)" % (key, val, supported[key]))
+            elif key not in ('allow_huge', 'num_cores', 'use_memmap', 'parallel', 'verbose', 'psf_pad', 'fft_pad',
+                             'save_to_tmp_dir'):
+                raise TypeError("unexpected keyword argument %r" % key)
+
+    @staticmethod
+    def _fft_semantics(convolve, default):
+        """Which astropy function the caller asked for: they differ only where a kernel window holds no valid
+        input (``convolve`` keeps the NaN, ``convolve_fft`` returns 0.0)."""
+        if convolve is None:
+            return default
+        name = getattr(convolve, '__name__', '')
+        if name == 'convolve_fft':
+            return True
+        if name == 'convolve':
+            return False
+        raise NotImplementedError("`convolve` must be astropy.convolution.convolve or convolve_fft (got %r): "
+                                  "the convolution runs on the device" % (convolve,))
+
+    def _convolve_epilogue(self, out, factor, nan_to_zero, skip=None):
+        """In place: ``out *= factor`` (Jy/beam rescale, :3376-3378 / :4230-4233), NaN -> 0 for ``convolve_fft``."""
+        if factor == 1.0 and not nan_to_zero:
+            return
+        lib = _lib.load()
+        dtype = _lib.F64 if out.dtype == _torch().float64 else _lib.F32
+        nchan, ny, nx = out.shape
+        _lib.check(lib.sc_scale(out.data_ptr(), dtype, nchan, ny, nx, out.stride(0), out.stride(1), float(factor),
+                                1 if nan_to_zero else 0, skip.data_ptr() if skip is not None else None, _stream()))
+
+    def convolve_to(self, beam, convolve=None, update_function=None, **kwargs):
+        """Convolve each channel in the cube to a specified beam; returns a cube with that ``beam``.
+
+        The kernel is ``beam.deconvolve(self.beam).as_kernel(pixscale)``; values in Jy/beam are rescaled by
+        ``beam.sr / self.beam.sr``.  ``convolve`` is accepted for drop-in compatibility: with the defaults both
+        astropy functions compute the same NaN-interpolating, zero-padded, normalised convolution the device
+        kernels do."""
+        self._check_convolve_kwargs(kwargs)
+        beam = Beam.coerce(beam)
+        if beam == self.beam:
+            warnings.warn("The given beam is identical to the current beam. "
+                          "Skipping convolution.")
+            return self
+        kernel = beam.deconvolve(self.beam).as_kernel(self._pixscale_deg())
+        factor = beam.sr / self.beam.sr if self._is_jybeam() else 1.0
+        fft = self._fft_semantics(convolve, default=not self._mirrors_dask)      # :3336 / dask:1412 defaults
+        out = self._run_spatial_smooth(self._kernel_array(kernel, 2), _lib.F32)
+        # planes copied through (:169-172) are neither rescaled nor zeroed
+        self._convolve_epilogue(out, factor, fft, skip=self._passthrough_flags)
+        cube = self._new_cube_with(data=out) if self._mirrors_dask else self._new_cube_reporting_f64(out)
+        cube._attach_beam(beam)
+        return cube
 
     # -- spectral resampling (spectral_cube.py:3224-3332; dask_spectral_cube.py:1250-1373) --------------
     def spectral_interpolate(self, spectral_grid, suppress_smooth_warning=False, fill_value=None,
@@ -929,6 +1045,15 @@ class SpectralCube(BaseSpectralCube):
         super(SpectralCube, self).__init__(data=data, wcs=wcs, mask=mask, meta=meta,
                                            fill_value=fill_value, header=header,
                                            allow_huge_operations=allow_huge_operations, **kwargs)
+        # beam loading happens after the WCS is read (spectral_cube.py:3716-3731; cube_utils.try_load_beam)
+        if beam is None:
+            if 'BMAJ' in self._header:
+                beam = Beam.from_fits_header(self._header)
+            elif isinstance(self._meta.get('beam'), Beam):
+                beam = self._meta['beam']
+        else:
+            beam = Beam.coerce(beam)
+        self._attach_beam(beam)
 
     @classmethod
     def read(cls, filename, format='fits', use_dask=False, **kwargs):
@@ -976,6 +1101,203 @@ class DaskSpectralCube(SpectralCube):
         if save_to_tmp_dir:
             cube._data
         return cube
+
+
+class BeamWarning(SpectralCubeWarning):
+    pass
+
+
+class NonFiniteBeamsWarning(SpectralCubeWarning):
+    pass
+
+
+class VaryingResolutionSpectralCube(BaseSpectralCube):
+    """A cube with one beam per channel (spectral_cube.py:3767-3894, base_class.py:476-542): ``beams`` is a
+    ``Beams`` / list of ``Beam``, or ``beam_table`` a mapping / record array with BMAJ, BMIN (arcsec) and BPA
+    (deg) columns.  ``use_dask=True`` gives the dask-mirroring variant (:3777-3782)."""
+
+    def __new__(cls, *args, **kwargs):
+        if kwargs.pop('use_dask', False) and cls is VaryingResolutionSpectralCube:
+            return super(VaryingResolutionSpectralCube, cls).__new__(DaskVaryingResolutionSpectralCube)
+        return super(VaryingResolutionSpectralCube, cls).__new__(cls)
+
+    def __init__(self, *args, **kwargs):
+        beam_table = kwargs.pop('beam_table', None)
+        beams = kwargs.pop('beams', None)
+        self.beam_threshold = kwargs.pop('beam_threshold', 0.01)
+        goodbeams_mask = kwargs.pop('goodbeams_mask', None)
+        kwargs.pop('use_dask', None)
+        kwargs.pop('wcs_tolerance', None)
+        if beam_table is None and beams is None:
+            raise ValueError("Must give either a beam table or a list of beams to "
+                             "initialize a VaryingResolutionSpectralCube")
+        super(VaryingResolutionSpectralCube, self).__init__(*args, **kwargs)
+        if beam_table is not None:
+            # CASA beam tables are in arcsec (:3838-3846)
+            beams = Beams.from_arcsec(np.asarray(beam_table['BMAJ'], dtype=np.float64),
+                                      np.asarray(beam_table['BMIN'], dtype=np.float64),
+                                      np.asarray(beam_table['BPA'], dtype=np.float64))
+            good = beams.isfinite
+            self._goodbeams_mask = good
+            if not np.all(good):
+                warnings.warn("There were {0} non-finite beams; layers with "
+                              "non-finite beams will be masked out.".format(np.count_nonzero(~good)),
+                              NonFiniteBeamsWarning)
+            beam_mask = BooleanArrayMask(good[:, None, None], self._wcs, shape=self.shape)
+            self._mask = beam_mask if self._mask is None else self._mask & beam_mask
+        if not isinstance(beams, Beams):
+            beams = Beams(beams)
+        if len(beams) != self.shape[0]:
+            raise ValueError("Beam list must have same size as spectral "
+                             "dimension")
+        self._beams = beams
+        if goodbeams_mask is not None:
+            self.goodbeams_mask = goodbeams_mask
+
+    # -- MultiBeamMixinClass (base_class.py:476-542) ------------------------------------------------
+    @property
+    def beams(self):
+        return self._beams[self.goodbeams_mask]
+
+    @property
+    def unmasked_beams(self):
+        return self._beams
+
+    @property
+    def goodbeams_mask(self):
+        if getattr(self, '_goodbeams_mask', None) is not None:
+            return self._goodbeams_mask
+        return self._beams.isfinite
+
+    @goodbeams_mask.setter
+    def goodbeams_mask(self, value):
+        value = np.asarray(value, dtype=bool)
+        if value.size != self.shape[0]:
+            raise ValueError("The 'good beams' mask must have the same size "
+                             "as the cube's spectral dimension")
+        self._goodbeams_mask = value
+
+    def _new_cube_with(self, **kw):
+        cube = BaseSpectralCube._new_cube_with(self, **kw)
+        if isinstance(cube, VaryingResolutionSpectralCube):
+            cube._beams = kw.get('beams', self._beams)
+            cube._goodbeams_mask = kw.get('goodbeams_mask', getattr(self, '_goodbeams_mask', None))
+            cube.beam_threshold = self.beam_threshold
+        return cube
+
+    def __getitem__(self, view):
+        from .masks import _slice3
+        cube = BaseSpectralCube.__getitem__(self, view)
+        spec = _slice3(view)[0]
+        cube._beams = self._beams[spec]
+        if getattr(self, '_goodbeams_mask', None) is not None:
+            cube._goodbeams_mask = self._goodbeams_mask[spec]
+        return cube
+
+    def mask_channels(self, goodchannels):
+        """:4270-4300 -- the beams of the masked channels are skipped by ``convolve_to``."""
+        goodchannels = np.asarray(goodchannels, dtype='bool')
+        if goodchannels.ndim != 1:
+            raise ValueError("goodchannels mask must be one-dimensional")
+        if goodchannels.size != self.shape[0]:
+            raise ValueError("goodchannels must have a length equal to the "
+                             "cube's spectral dimension.")
+        cube = self.with_mask(goodchannels[:, None, None])
+        cube.goodbeams_mask = np.logical_and(goodchannels, self.goodbeams_mask)
+        return cube
+
+    def spectral_interpolate(self, *args, **kwargs):
+        raise AttributeError("VaryingResolutionSpectralCubes can't be "
+                             "spectrally interpolated.  Convolve to a "
+                             "common resolution with `convolve_to` before "
+                             "attempting spectral interpolation.")
+
+    def spectral_smooth(self, *args, **kwargs):
+        raise AttributeError("VaryingResolutionSpectralCubes can't be "
+                             "spectrally smoothed.  Convolve to a "
+                             "common resolution with `convolve_to` before "
+                             "attempting spectral smoothed.")
+
+    # -- convolve_to (:4127-4240; dask_spectral_cube.py:1512-1630) ----------------------------------
+    _result_class = None       # set below: SpectralCube / DaskSpectralCube
+
+    def _channel_plan(self, beam, allow_smaller):
+        """Per channel: (kernel array or None, Jy/beam factor), following the reference's loop (:4186-4209)."""
+        pixscale = self._pixscale_deg()
+        jybeam = self._is_jybeam()
+        plan = []
+        for bm, valid in zip(self.unmasked_beams, self.goodbeams_mask):
+            if not valid or beam == bm:
+                plan.append((None, 1.0))        # masked-out beams are skipped; equal beams are a point response
+                continue
+            try:
+                kernel = beam.deconvolve(bm).as_kernel(pixscale)
+                plan.append((self._kernel_array(kernel, 2), beam.sr / bm.sr if jybeam else 1.0))
+            except ValueError:
+                if not allow_smaller:
+                    raise
+                plan.append((None, 1.0))
+        return plan
+
+    def convolve_to(self, beam, allow_smaller=False, convolve=None, update_function=None, **kwargs):
+        """Convolve each channel in the cube to a specified beam; returns a single-beam cube.
+
+        Every channel has its own deconvolved kernel; each plane is one launch of the spatial kernels writing
+        its slice of the result (the planes of a real cube are tens of MB: the launches fill the chip), followed
+        by the in-place Jy/beam rescale of that plane."""
+        self._check_convolve_kwargs(kwargs)
+        beam = Beam.coerce(beam)
+        pc = self._wcs.pc
+        if pc[0, 1] != 0 or pc[1, 0] != 0:
+            warnings.warn("The beams will produce convolution kernels "
+                          "that are not aware of any misaligment "
+                          "between pixel and world coordinates, "
+                          "and there are off-diagonal elements of the "
+                          "WCS spatial transformation matrix.  "
+                          "Unexpected results are likely.", BeamWarning)
+        plan = self._channel_plan(beam, allow_smaller)
+        fft = self._fft_semantics(convolve, default=not self._mirrors_dask)      # :4128 / dask:1513 defaults
+        torch = _torch()
+        lib = _lib.load()
+        nchan, ny, nx = self.shape
+        out = torch.empty((nchan, ny, nx), dtype=torch.float32, device=self._data.device)
+        fill = float(self._fill_value)
+        for ii, (k2d, factor) in enumerate(plan):
+            plane = BaseSpectralCube.__getitem__(self, (slice(ii, ii + 1), slice(None), slice(None)))
+            dst = out[ii:ii + 1]
+            if k2d is None:
+                # newdata[ii] = img, the FILLED plane (:4222-4225)
+                src = plane._data
+                if plane._mask is None:
+                    dst.copy_(src)
+                else:
+                    desc, keep = plane._mask_desc()
+                    _lib.check(lib.sc_fill_masked(src.data_ptr(), 1, ny, nx, src.stride(0), src.stride(1), desc,
+                                                  fill, dst.data_ptr(), _stream()))
+            else:
+                plane._run_spatial_smooth(k2d, _lib.F32, out=dst, passthrough=0)
+                self._convolve_epilogue(dst, factor, fft)
+            if update_function is not None:
+                update_function()
+        cube = BaseSpectralCube._new_cube_with(self, data=out, cls=self._result_class, beam=beam)
+        if not cube._mirrors_dask:
+            cube._hi_is_widened_f32 = True       # the reference's buffer is float64 (:4214)
+        return cube
+
+
+class DaskVaryingResolutionSpectralCube(VaryingResolutionSpectralCube):
+    """dask_spectral_cube.py:1467-1650"""
+    _mirrors_dask = True
+
+    def use_dask_scheduler(self, scheduler, num_workers=None):
+        return _NullContext()
+
+    def rechunk(self, *args, **kwargs):
+        return self
+
+
+VaryingResolutionSpectralCube._result_class = SpectralCube
+DaskVaryingResolutionSpectralCube._result_class = DaskSpectralCube
 
 
 class _NullContext(object):
