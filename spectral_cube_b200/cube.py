@@ -600,6 +600,14 @@ class BaseSpectralCube(object):
         raise NotImplementedError("`convolve` must be astropy.convolution.convolve or convolve_fft (got %r): "
                                   "the convolution runs on the device" % (convolve,))
 
+    def _convolved_denominator_counts(self):
+        """Device {missing, sampled} = {1, 1}: makes the separable path take the kernel whose denominator is the
+        validity map convolved with the float32 factors.  Beam kernels are 16 sigma wide: their outer taps fall
+        below the 2^-31 quantum of the sparse-deficit kernel's integer denominator, which would lose the
+        interpolation weight of outputs that only such taps connect to valid data (deep inside blank regions)."""
+        torch = _torch()
+        return torch.ones((2,), dtype=torch.int32, device=self._data.device)
+
     def _convolve_epilogue(self, out, factor, nan_to_zero, skip=None):
         """In place: ``out *= factor`` (Jy/beam rescale, :3376-3378 / :4230-4233), NaN -> 0 for ``convolve_fft``."""
         if factor == 1.0 and not nan_to_zero:
@@ -626,7 +634,8 @@ class BaseSpectralCube(object):
         kernel = beam.deconvolve(self.beam).as_kernel(self._pixscale_deg())
         factor = beam.sr / self.beam.sr if self._is_jybeam() else 1.0
         fft = self._fft_semantics(convolve, default=not self._mirrors_dask)      # :3336 / dask:1412 defaults
-        out = self._run_spatial_smooth(self._kernel_array(kernel, 2), _lib.F32)
+        out = self._run_spatial_smooth(self._kernel_array(kernel, 2), _lib.F32,
+                                       strategy_counts=self._convolved_denominator_counts())
         # planes copied through (:169-172) are neither rescaled nor zeroed
         self._convolve_epilogue(out, factor, fft, skip=self._passthrough_flags)
         cube = self._new_cube_with(data=out) if self._mirrors_dask else self._new_cube_reporting_f64(out)
@@ -1262,6 +1271,7 @@ class VaryingResolutionSpectralCube(BaseSpectralCube):
         nchan, ny, nx = self.shape
         out = torch.empty((nchan, ny, nx), dtype=torch.float32, device=self._data.device)
         fill = float(self._fill_value)
+        counts = self._convolved_denominator_counts()
         for ii, (k2d, factor) in enumerate(plan):
             plane = BaseSpectralCube.__getitem__(self, (slice(ii, ii + 1), slice(None), slice(None)))
             dst = out[ii:ii + 1]
@@ -1275,7 +1285,7 @@ class VaryingResolutionSpectralCube(BaseSpectralCube):
                     _lib.check(lib.sc_fill_masked(src.data_ptr(), 1, ny, nx, src.stride(0), src.stride(1), desc,
                                                   fill, dst.data_ptr(), _stream()))
             else:
-                plane._run_spatial_smooth(k2d, _lib.F32, out=dst, passthrough=0)
+                plane._run_spatial_smooth(k2d, _lib.F32, out=dst, passthrough=0, strategy_counts=counts)
                 self._convolve_epilogue(dst, factor, fft)
             if update_function is not None:
                 update_function()

@@ -230,6 +230,29 @@ def test_convolve_choice_decides_what_an_empty_window_gives():
         sc.convolve_to(target, convolve=lambda a, k: a)
 
 
+@use_dask
+def test_round_beams_keep_the_interpolation_weight_deep_inside_blank_regions(use_dask):
+    """Round beams take the separable kernels.  Their 16 sigma wide factors have outer taps down to e^-32: outputs
+    several sigma inside a blank region hang on those taps alone, and must still be the exact weighted mean."""
+    data = _random_cube((2, 64, 80), seed=17, nan_frac=0.01)
+    data[:, 12:52, 14:66] = np.nan                         # wider than the 15 x 15 kernel
+    sc, oc = pair(data, use_dask, beam=(3.0, 3.0, 0.0))
+    got = sc.convolve_to(scb().Beam.from_arcsec(5.0), convolve=None if use_dask else _named('convolve')).unmasked_data[:]
+    want = oc.convolve_to(OBeam.arcsec(5.0), convolve=oconv.convolve)._data
+    kernel = OBeam.arcsec(5.0).deconvolve(OBeam.arcsec(3.0)).as_kernel(abs(G.ADV_WCS['cdelt'][1]))
+    assert kernel.shape == (15, 15)
+    weight = np.stack([oconv.convolve(np.where(np.isnan(p), -1.0, 0.0), kernel) + 1.0 for p in data.astype(float)])
+    assert np.isnan(want).any() and ((weight < 1e-9) & ~np.isnan(want)).any()      # the fringe exists
+    assert_maps_close(got, want, rtol=RTOL, atol=1e-6, what='round beam, blank block')
+
+
+def _named(name):
+    def fn(array, kernel, **kw):
+        raise AssertionError("never called: only its name is read")
+    fn.__name__ = name
+    return fn
+
+
 def test_planes_copied_through_are_neither_rescaled_nor_zeroed():
     """numpy class: a channel with nothing included by the mask is returned as it is, filled
     (spectral_cube.py:161-172), without the Jy/beam factor; the dask class convolves it like any other."""
