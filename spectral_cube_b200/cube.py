@@ -1056,10 +1056,13 @@ class SpectralCube(BaseSpectralCube):
                                            allow_huge_operations=allow_huge_operations, **kwargs)
         # beam loading happens after the WCS is read (spectral_cube.py:3716-3731; cube_utils.try_load_beam)
         if beam is None:
-            if 'BMAJ' in self._header:
-                beam = Beam.from_fits_header(self._header)
-            elif isinstance(self._meta.get('beam'), Beam):
+            if isinstance(self._meta.get('beam'), Beam):
                 beam = self._meta['beam']
+            else:
+                try:                                          # cube_utils.try_load_beam: no beam is fine
+                    beam = Beam.from_fits_header(self._header)
+                except Exception:
+                    beam = None
         else:
             beam = Beam.coerce(beam)
         self._attach_beam(beam)

@@ -1,6 +1,6 @@
 """
 Throughput of every BASELINE.json config beyond the headline one (bench.py covers configs[1]).
-Run on the GPU box:   python tools/bench_configs.py [c1] [c3] [c4] [c5]
+Run on the GPU box:   python tools/bench_configs.py [c1] [c3] [c4] [c5] [reduce] [ingest] [convolve] [target]
               or   python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py c4 c5
 Prints one JSON line per measurement (rank 0).  Timing: CUDA events, warm-up 2, mean of 5, max over ranks.
 """
@@ -163,6 +163,39 @@ if 'reduce' in which and world == 1:
     ms = timeit(lambda: c._reduce_axis0_raw({'max'}))
     emit('reduce', 'max along the spectral axis (peak map)', V, ms, 4 * V + 4 * ny * nx)
     del dev, c
+    torch.cuda.empty_cache()
+
+if 'convolve' in which and world == 1:
+    # convolve_to.  Round beams -> the separable kernels (+ the sc_scale epilogue for Jy/beam),
+    # rotated elliptical beams -> direct2d_kernel, per-channel beams -> one launch pair per plane.
+    nchan, ny, nx = 64, 4096, 4096
+    V = nchan * ny * nx
+    dev = synth_cube(nchan, ny, nx, border=102)
+    w = benchmark_wcs(nchan, ny, nx)
+    pix = float(np.sqrt(abs(np.linalg.det(w.pixel_scale_matrix[:2, :2]))))
+    for unit in ('K', 'Jy/beam'):
+        c = scb.SpectralCube(dev, w, unit=unit, beam=scb.Beam(3 * pix))
+        c._mask = scb.LazyMask(np.isfinite, cube=c)
+        ms = timeit(lambda: c.convolve_to(scb.Beam(5 * pix)), n=3, warm=1)
+        emit('convolve', 'convolve_to, round 3 px -> 5 px beam (29x29 separable, convolved denominator), unit %s, 4096x4096x64' % unit,
+             V, ms, (8 + 8) * V)
+        c = scb.SpectralCube(dev, w, unit=unit, beam=scb.Beam(3 * pix, 2 * pix, 60.0))
+        c._mask = scb.LazyMask(np.isfinite, cube=c)
+        k = scb.Beam(5 * pix, 4 * pix, 25.0).deconvolve(c.beam).as_kernel(pix)
+        ms = timeit(lambda: c.convolve_to(scb.Beam(5 * pix, 4 * pix, 25.0)), n=2, warm=1)
+        emit('convolve', 'convolve_to, rotated elliptical beams (%dx%d taps, direct2d_kernel), unit %s' % (k.shape + (unit,)), V, ms, (8 + 8) * V)
+    rng = np.random.default_rng(0)
+    beams = scb.Beams(major=rng.uniform(2.5, 3.5, nchan) * pix, minor=rng.uniform(2.0, 2.5, nchan) * pix, pa=rng.uniform(0, 180, nchan))
+    vr = scb.VaryingResolutionSpectralCube(dev, w, unit='Jy/beam', beams=beams)
+    vr._mask = scb.LazyMask(np.isfinite, cube=vr)
+    ms = timeit(lambda: vr.convolve_to(scb.Beam(5 * pix)), n=2, warm=1)
+    emit('convolve', 'VaryingResolutionSpectralCube.convolve_to, %d per-channel elliptical beams -> round 5 px, Jy/beam' % nchan, V, ms, (8 + 8) * V)
+    lib = _lib.load()
+    out = torch.empty((nchan, ny, nx), dtype=torch.float32, device='cuda')
+    ms = timeit(lambda: _lib.check(lib.sc_scale(out.data_ptr(), _lib.F32, nchan, ny, nx, out.stride(0), out.stride(1), 1.0000001, 1, None,
+                                                torch.cuda.current_stream().cuda_stream)))
+    emit('convolve', 'sc_scale alone (in place, float32)', V, ms, 8 * V)
+    del dev, c, vr, out
     torch.cuda.empty_cache()
 
 if 'ingest' in which and world == 1:
