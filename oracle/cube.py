@@ -223,6 +223,18 @@ class OracleCube(object):
     def argmin(self, axis=None):
         return self._apply_numpy_function(np.nanargmin, fill=np.inf, axis=axis)        # :815-826
 
+    def statistics(self):
+        """dask_spectral_cube.py:769-814 (one chunk = the whole cube; the dtype of the data is kept like there)."""
+        chunk = self._get_filled_data(fill=np.nan)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            stats = {'npts': np.sum(~np.isnan(chunk)), 'min': np.nanmin(chunk), 'max': np.nanmax(chunk),
+                     'sum': np.nansum(chunk), 'sumsq': np.nansum(chunk * chunk)}
+            stats['mean'] = stats['sum'] / stats['npts']
+            stats['sigma'] = ((stats['sumsq'] - stats['sum'] ** 2 / stats['npts']) / (stats['npts'] - 1)) ** 0.5
+            stats['rms'] = np.sqrt(stats['sumsq'] / stats['npts'])
+        return stats
+
     # -- moments -------------------------------------------------------------------------------
     def moment(self, order=0, axis=0, how='auto'):
         if axis == 0 and order == 2:

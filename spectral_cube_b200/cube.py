@@ -78,6 +78,26 @@ def whole_std(torch, sum_map, count_map, m2_map, ddof=0):
     return float(np.sqrt(m2 / (n - ddof)))
 
 
+def whole_statistics(torch, sum_map, count_map, m2_map, min_map, max_map):
+    """The dictionary of ``DaskSpectralCube.statistics`` (dask_spectral_cube.py:769-814, CASA's ia.statistics names)
+    from the per-spaxel partials.  ``sumsq`` is rebuilt without cancellation as sum_i (m2_i + s_i^2 / n_i); ``sigma``
+    follows the reference's textbook formula on these sums."""
+    n_i = count_map.to(torch.float64)
+    ok = n_i > 0
+    zero = torch.zeros_like(n_i)
+    npts = int(count_map.sum().item())
+    s_i = torch.where(ok, sum_map, zero)
+    total = float(s_i.sum().item())
+    sumsq = float(torch.where(ok, m2_map + s_i * s_i / torch.clamp(n_i, min=1.0), zero).sum().item())
+    stats = {'npts': npts, 'min': whole_extremum(torch, min_map, 'min'), 'max': whole_extremum(torch, max_map, 'max'),
+             'sum': total, 'sumsq': sumsq}
+    with np.errstate(invalid='ignore', divide='ignore'):
+        stats['mean'] = float(np.float64(total) / npts)
+        stats['sigma'] = float(np.sqrt((np.float64(sumsq) - np.float64(total) ** 2 / npts) / (npts - 1)))
+        stats['rms'] = float(np.sqrt(np.float64(sumsq) / npts))
+    return stats
+
+
 def whole_extremum(torch, ext_map, which):
     ok = ~torch.isnan(ext_map)
     if not bool(ok.any()):
@@ -1101,6 +1121,13 @@ class DaskSpectralCube(SpectralCube):
 
     def _smooth_fill(self):
         return np.nan                        # dask_spectral_cube.py:816, 823
+
+    def statistics(self):
+        """Global basic statistics of the data (dask_spectral_cube.py:769-814): npts, min, max, sum, sumsq, mean,
+        sigma, rms -- ONE pass over the cube (`sc_reduce_axis0`), combined on the (ny, nx) partial maps.  Values
+        are plain floats in the cube's unit (its square for sumsq); the reference wraps them in Quantities."""
+        r = self._reduce_axis0_raw({'sum', 'count', 'm2', 'min', 'max'})
+        return whole_statistics(_torch(), r['sum'], r['count'], r['m2'], r['min'], r['max'])
 
     def spectral_smooth(self, kernel, convolve=None, save_to_tmp_dir=False, **kwargs):
         """Lazy like the reference's dask class; ``save_to_tmp_dir=True`` computes straight away."""

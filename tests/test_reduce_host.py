@@ -76,3 +76,31 @@ def test_oracle_whole_cube_reductions_are_the_numpy_nan_functions():
     assert np.isclose(oc.sum(), np.nansum(filled)) and np.isclose(oc.mean(), np.nanmean(filled))
     assert np.isclose(oc.std(), np.nanstd(filled)) and oc.max() == np.nanmax(filled) and oc.min() == np.nanmin(filled)
     assert np.isnan(OracleCube(np.full((2, 2, 2), np.nan, dtype=np.float32), OWCS(**WCS), unit='K').sum())
+
+
+@pytest.mark.parametrize('seed', [0, 3])
+def test_statistics_from_partials(seed):
+    """`DaskSpectralCube.statistics` (dask_spectral_cube.py:769-814) from the partial maps of one pass."""
+    rng = np.random.default_rng(seed)
+    data = (1.5 + rng.normal(0, 2, (17, 6, 9))).astype(np.float32)
+    data[rng.random(data.shape) < 0.1] = np.nan
+    data[:, 0, :] = np.nan
+    r = partials(data)
+    got = C.whole_statistics(torch, r['sum'], r['count'], r['m2'], r['min'], r['max'])
+    d = data.astype(np.float64)
+    n = int((~np.isnan(d)).sum())
+    want = {'npts': n, 'min': np.nanmin(d), 'max': np.nanmax(d), 'sum': np.nansum(d), 'sumsq': np.nansum(d * d)}
+    want['mean'] = want['sum'] / n
+    want['sigma'] = np.sqrt((want['sumsq'] - want['sum'] ** 2 / n) / (n - 1))
+    want['rms'] = np.sqrt(want['sumsq'] / n)
+    assert set(got) == set(want) and got['npts'] == n
+    for key in want:
+        assert np.isclose(got[key], want[key], rtol=1e-12), key
+    # the oracle restates the reference in the data's own float32 (one chunk): same numbers to float32 accuracy
+    oc = OracleCube(data, OWCS(**WCS), unit='K', use_dask=True).statistics()
+    for key in want:
+        assert np.isclose(oc[key], want[key], rtol=2e-6), key
+    blank = partials(np.full((4, 3, 4), np.nan, dtype=np.float32))
+    got = C.whole_statistics(torch, blank['sum'], blank['count'], blank['m2'], blank['min'], blank['max'])
+    assert got['npts'] == 0 and got['sum'] == 0.0 and got['sumsq'] == 0.0
+    assert all(np.isnan(got[k]) for k in ('min', 'max', 'mean', 'sigma', 'rms'))

@@ -310,3 +310,22 @@ def test_sc_scale_through_the_c_abi():
     want[1, :, 8:24] = (want[1, :, 8:24].astype(np.float64) * -3.0).astype(np.float32)
     np.testing.assert_array_equal(dev.cpu().numpy(), want)
     assert lib.sc_scale(None, _lib.F32, 1, 1, 1, 1, 1, 2.0, 0, None, stream) != 0
+
+
+# ---- DaskSpectralCube.statistics (dask_spectral_cube.py:769-814) ---------------------------
+@pytest.mark.parametrize('maskname', ['isfinite', 'gt'])
+def test_statistics(maskname):
+    data = (1.5 + _random_cube((24, 40, 52), seed=8, nan_frac=0.05)).astype(np.float32)
+    sc, oc = gpu_cube(data, G.ADV_WCS, use_dask=True), oracle_cube(data, G.ADV_WCS, use_dask=True)
+    if maskname == 'gt':
+        sc, oc = sc.with_mask(sc > 1.0), oc.with_mask(oc > 1.0)
+    got, want = sc.statistics(), oc.statistics()
+    assert set(got) == {'npts', 'min', 'max', 'sum', 'sumsq', 'mean', 'sigma', 'rms'} == set(want)
+    assert got['npts'] == int(want['npts']) and got['min'] == float(want['min']) and got['max'] == float(want['max'])
+    # the reference sums in the data's float32 (pairwise); exact values in float64 here
+    filled = np.where(oc._mask_include(), data, np.nan).astype(np.float64)
+    for key, exact in (('sum', np.nansum(filled)), ('sumsq', np.nansum(filled * filled))):
+        assert np.isclose(got[key], exact, rtol=1e-12), key
+    for key in ('sum', 'sumsq', 'mean', 'sigma', 'rms'):
+        assert np.isclose(got[key], float(want[key]), rtol=RTOL), (key, got[key], want[key])
+    assert not hasattr(gpu_cube(data, G.ADV_WCS, use_dask=False), 'statistics')      # the dask class only
