@@ -1,7 +1,8 @@
 """
 Host plumbing of `convolve_to` without a device: tensors stay on the host, the REAL libsc_b200.so is called, so
 ctypes marshals every argument and the library's own argument validation (SC_CHECK_ARG) runs; each call then stops
-at its first CUDA API call ("no device"), which is tolerated here and only here.  What this pins: class
+at its first CUDA API call ("no device"), which is tolerated here and only here (the `host` fixture of
+tests/conftest.py).  What this pins: class
 construction and beam propagation, the per-channel plan of VaryingResolutionSpectralCube, which C-ABI entry
 points a call reaches and in what number, and that the library accepts the shapes / strides / flags it is given.
 Numerical parity is the GPU tests' business (tests/test_zz_convolve_to_gpu.py).
@@ -12,31 +13,6 @@ import numpy as np
 import pytest
 
 from tests.golden import reference_goldens as G
-
-
-@pytest.fixture
-def host(monkeypatch):
-    import torch
-    import spectral_cube_b200 as S
-    from spectral_cube_b200 import cube as C, _lib
-
-    class _Stream(object):
-        cuda_stream = 0
-
-    calls = []
-
-    def check(rc):
-        msg = _lib.load().sc_last_error().decode() if rc else ''
-        calls.append((rc, msg))
-        if rc and 'CUDA error' not in msg:
-            raise AssertionError("the library refused the arguments: %d %s" % (rc, msg))
-
-    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
-    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _Stream())
-    monkeypatch.setattr(_lib, 'require_cuda', lambda: torch)
-    monkeypatch.setattr(_lib, 'check', check)
-    monkeypatch.setattr(C, '_stream', lambda: 0)
-    return S, calls
 
 
 def make(S, data, use_dask, beam=None, unit='K'):
