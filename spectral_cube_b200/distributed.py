@@ -245,8 +245,23 @@ class RowShardedCube(object):
         dist = _dist()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        # numpy class: `_apply_spatial_function` copies a channel image through when the mask includes nothing of
+        # the WHOLE image (spectral_cube.py:161-172).  A shard cannot take that decision on its own rows -- a plane
+        # blank here may have data next door that reaches across the boundary through the halo rows -- so shards
+        # always convolve.  A plane blank everywhere convolves to what the copy would give for the usual fill values
+        # (NaN stays NaN, 0 stays 0); for any other finite fill the job-wide blank planes are copied afterwards.
+        sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        passthrough = 0 if (sharded and not dask) else None
         out = loc._run_spatial_smooth(k2d, _lib.F32, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h,
-                                      strategy_counts=counts)
+                                      strategy_counts=counts, passthrough=passthrough)
+        fill = float(loc._fill_value)
+        if sharded and not dask and loc._mask is not None and np.isfinite(fill) and fill != 0.0:
+            inc = loc._mask._include_tensor(src)
+            blank = (~inc.reshape(nchan, -1).any(dim=1)).to(torch.int32)
+            dist.all_reduce(blank, op=dist.ReduceOp.MIN, group=self.group)
+            blank = blank.bool()
+            if bool(blank.any()):
+                out[blank] = loc._filled_tensor(fill)[blank]
         new = loc._new_cube_with(data=out) if dask else loc._new_cube_reporting_f64(out)
         return self._wrap(new)
 
