@@ -491,14 +491,18 @@ class BaseSpectralCube(object):
                                  " To ignore this error, set `raise_error_jybm=False`.")
 
     @staticmethod
-    def _separable_factors(k2d):
-        """(ky, kx) if the 2-D kernel is an outer product to float64 rounding, else None."""
+    def _separable_factors(k2d, every_tap=False):
+        """(ky, kx) if the 2-D kernel is an outer product to float64 rounding, else None.  ``every_tap``: the
+        product has to reproduce each tap to 1e-12 of ITSELF, not of the largest one -- beam kernels are 16 sigma
+        wide and outputs deep inside blank regions hang on taps of 1e-20 and less (a rotated sub-pixel ellipse is an
+        outer product to 1e-14 of its peak and nothing like one out there)."""
         cy, cx = k2d.shape[0] // 2, k2d.shape[1] // 2
         piv = k2d[cy, cx]
         if piv == 0:
             return None
         ky, kx = k2d[:, cx].copy(), k2d[cy, :] / piv
-        if np.max(np.abs(np.outer(ky, kx) - k2d)) <= 1e-14 * np.max(np.abs(k2d)):
+        err = np.abs(np.outer(ky, kx) - k2d)
+        if (np.all(err <= 1e-12 * np.abs(k2d)) if every_tap else np.max(err) <= 1e-14 * np.max(np.abs(k2d))):
             return ky, kx
         return None
 
@@ -515,7 +519,7 @@ class BaseSpectralCube(object):
         return counts
 
     def _run_spatial_smooth(self, k2d, out_dtype, halo_top=None, halo_bot=None, halo_rows=0, strategy_counts=None,
-                            out=None, passthrough=None):
+                            out=None, passthrough=None, every_tap=False):
         """`out` may be a (nchan, ny, nx) view of a larger tensor (x stride 1): `convolve_to` on per-channel
         beams writes each channel plane of one result cube with its own kernel."""
         torch = _torch()
@@ -536,7 +540,7 @@ class BaseSpectralCube(object):
         # the library leaves the per-channel "copied through" flags in the workspace behind the taps
         self._passthrough_flags = (ws[k2d.size * 8 + 512: k2d.size * 8 + 512 + nchan]
                                    if passthrough and desc.n_nodes > 0 else None)
-        sep = self._separable_factors(k2d)
+        sep = self._separable_factors(k2d, every_tap=every_tap)
         if sep is not None:
             (ya, yp), (xa, xp) = _lib.as_double_array(sep[0]), _lib.as_double_array(sep[1])
             sc = strategy_counts.data_ptr() if strategy_counts is not None else None
@@ -654,7 +658,7 @@ class BaseSpectralCube(object):
         kernel = beam.deconvolve(self.beam).as_kernel(self._pixscale_deg())
         factor = beam.sr / self.beam.sr if self._is_jybeam() else 1.0
         fft = self._fft_semantics(convolve, default=not self._mirrors_dask)      # :3336 / dask:1412 defaults
-        out = self._run_spatial_smooth(self._kernel_array(kernel, 2), _lib.F32,
+        out = self._run_spatial_smooth(self._kernel_array(kernel, 2), _lib.F32, every_tap=True,
                                        strategy_counts=self._convolved_denominator_counts())
         # planes copied through (:169-172) are neither rescaled nor zeroed
         self._convolve_epilogue(out, factor, fft, skip=self._passthrough_flags)
@@ -1315,7 +1319,7 @@ class VaryingResolutionSpectralCube(BaseSpectralCube):
                     _lib.check(lib.sc_fill_masked(src.data_ptr(), 1, ny, nx, src.stride(0), src.stride(1), desc,
                                                   fill, dst.data_ptr(), _stream()))
             else:
-                plane._run_spatial_smooth(k2d, _lib.F32, out=dst, passthrough=0, strategy_counts=counts)
+                plane._run_spatial_smooth(k2d, _lib.F32, out=dst, passthrough=0, strategy_counts=counts, every_tap=True)
                 self._convolve_epilogue(dst, factor, fft)
             if update_function is not None:
                 update_function()
