@@ -720,6 +720,110 @@ direct2d_kernel(const __grid_constant__ DirectParams d) {
     else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
 }
 
+// ---- tiled direct 2-D kernel (OPT-IN: SC_DIRECT2D=1; written without a GPU at hand, not yet run on one) ----
+// What `convolve_to` needs for rotated elliptical beams, where direct2d_kernel pays one L1 request per tap and
+// output.  CTA = 256 threads = a 32-column x 64-row output tile of one channel; lane = column, warp = 8 rows.
+// The filled input box (tile + kernel margin) is staged ONCE in shared memory, widened to float64, with a float
+// validity plane (missing -> value 0, validity 0; zero padding outside the image is valid, as in astropy).
+// Each thread keeps 8 float64 numerators: for every kernel column it walks the kernel rows with a 16-deep
+// register window of its image column (1 LDS.64 + 1 LDS.32 + 1 broadcast tap per 8 DFMA + 8 FFMA); the
+// denominator is summed in float32 per kernel column and carried in float64 across columns.
+constexpr int DT_TX = 32, DT_TY = 64, DT_RY = 8;
+constexpr int DT_MAX_TAPS = 2048;                 // 45 x 45: taps + box fit the 227 KB of shared memory
+
+template <int OUT64>
+__global__ void __launch_bounds__(256)
+direct2d_tiled_kernel(const __grid_constant__ DirectParams d, int tiles_x, int tiles_y) {
+    const SpatialParams &p = d.sp;
+    extern __shared__ __align__(16) unsigned char dt_smem[];
+    const int nty = d.nty, ntx = d.ntx, hy = nty >> 1, hx = ntx >> 1;
+    const int bw = DT_TX + ntx - 1;                    // box width
+    const int bh = DT_TY + nty - 1 + DT_RY;            // box height (+ one window of never-used rows)
+    double *staps = reinterpret_cast<double *>(dt_smem);
+    double *sval = staps + ((nty * ntx + 1) & ~1);
+    float *sok = reinterpret_cast<float *>(sval + (size_t)bw * bh);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t b = blockIdx.x;
+    const int64_t tx_i = b % tiles_x; b /= tiles_x;
+    const int64_t ty_i = b % tiles_y;
+    const int64_t c = b / tiles_y;
+    const int64_t x0 = tx_i * DT_TX, y0 = ty_i * DT_TY;
+
+    for (int i = tid; i < nty * ntx; i += 256) staps[i] = d.taps[i];
+    for (int i = tid; i < bw * bh; i += 256) {
+        const int q = i / bw, pcol = i - q * bw;
+        const int64_t yy = y0 - hy + q, xx = x0 - hx + pcol;
+        float v = 0.0f;                                // zero padding: a valid sample
+        if (q < DT_TY + nty - 1 && xx >= 0 && xx < p.nx) {
+            if (yy >= 0 && yy < p.ny) {
+                v = __ldg(p.in + c * p.stride_c + yy * p.stride_y + xx);
+                if (!mask_include_rt(p.mask, v, c, yy, xx)) v = p.fill;
+            } else if (yy < 0 && p.halo_top && yy >= -p.halo_rows) {
+                v = __ldg(p.halo_top + (c * p.halo_rows + (p.halo_rows + yy)) * p.nx + xx);
+            } else if (yy >= p.ny && p.halo_bot && yy < p.ny + p.halo_rows) {
+                v = __ldg(p.halo_bot + (c * p.halo_rows + (yy - p.ny)) * p.nx + xx);
+            }
+        }
+        const bool good = v == v;
+        sval[i] = good ? (double)v : 0.0;
+        sok[i] = good ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+
+    const int r0 = warp * DT_RY;                       // first of this thread's 8 output rows (tile-local)
+    double top[DT_RY], botd[DT_RY];
+#pragma unroll
+    for (int j = 0; j < DT_RY; ++j) { top[j] = 0.0; botd[j] = 0.0; }
+    // out(r, x) = sum_{s, sx} K[nty-1-s][ntx-1-sx] * box[r + s][x + sx]
+    for (int sx = 0; sx < ntx; ++sx) {
+        const int kx = ntx - 1 - sx;
+        const double *colv = sval + (size_t)r0 * bw + lane + sx;
+        const float *colo = sok + (size_t)r0 * bw + lane + sx;
+        double a[2 * DT_RY];
+        float o[2 * DT_RY], botf[DT_RY];
+#pragma unroll
+        for (int j = 0; j < DT_RY; ++j) { a[j] = colv[(size_t)j * bw]; o[j] = colo[(size_t)j * bw]; botf[j] = 0.0f; }
+        for (int sb = 0; sb < nty; sb += DT_RY) {
+#pragma unroll
+            for (int j = 0; j < DT_RY; ++j) {
+                a[DT_RY + j] = colv[(size_t)(sb + DT_RY + j) * bw];
+                o[DT_RY + j] = colo[(size_t)(sb + DT_RY + j) * bw];
+            }
+#pragma unroll
+            for (int si = 0; si < DT_RY; ++si) {
+                if (sb + si < nty) {                   // uniform across the CTA
+                    const double k = staps[(nty - 1 - sb - si) * ntx + kx];
+                    const float kf = (float)k;
+#pragma unroll
+                    for (int j = 0; j < DT_RY; ++j) {
+                        top[j] = fma(k, a[j + si], top[j]);
+                        botf[j] = fmaf(kf, o[j + si], botf[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < DT_RY; ++j) { a[j] = a[DT_RY + j]; o[j] = o[DT_RY + j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < DT_RY; ++j) botd[j] += (double)botf[j];
+    }
+
+    const int64_t x = x0 + lane;
+    const bool pass = p.passthrough && p.passthrough[c];
+#pragma unroll
+    for (int j = 0; j < DT_RY; ++j) {
+        const int64_t y = y0 + r0 + j;
+        if (x < p.nx && y < p.ny) {
+            const size_t ci = (size_t)(r0 + j + hy) * bw + lane + hx;
+            const double centre = sok[ci] != 0.0f ? sval[ci] : nan64();
+            double res = (botd[j] == 0.0) ? centre : top[j] / botd[j];
+            if (pass) res = centre;
+            if (OUT64) reinterpret_cast<double *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = res;
+            else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
+        }
+    }
+}
+
 // flags[c] = 1 when no voxel of channel c is included by the mask: `_apply_spatial_function`
 // (spectral_cube.py:161-172) copies such a plane through instead of convolving it.  One CTA per
 // channel, early exit as soon as any thread sees an included voxel (the common case: first pass).
@@ -1036,6 +1140,24 @@ extern "C" int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
     DirectParams d{p, tdev, ntaps_y, ntaps_x};
     const int64_t total = nchan * ny * nx;
     LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
+    bool nonneg = true;                                  // the float32 zero test of the tiled kernel's denominator
+    for (int i = 0; i < nt; ++i) nonneg = nonneg && taps[i] / sum >= 0.0;
+    if (env_int("SC_DIRECT2D", 0) == 1 && nt <= DT_MAX_TAPS && nonneg) {
+        const int64_t tiles_x = cdiv(nx, DT_TX), tiles_y = cdiv(ny, DT_TY);
+        const int64_t grid = tiles_x * tiles_y * nchan;
+        SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
+        const size_t box = (size_t)(DT_TX + ntaps_x - 1) * (DT_TY + ntaps_y - 1 + DT_RY);
+        const size_t smem = (size_t)((nt + 1) & ~1) * 8 + box * 12;
+        if (out_dtype == SC_F64) {
+            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            direct2d_tiled_kernel<1><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
+        } else {
+            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            direct2d_tiled_kernel<0><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
+        }
+        SC_CUDA(cudaGetLastError());
+        return SC_OK;
+    }
     if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
     else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
     SC_CUDA(cudaGetLastError());

@@ -346,3 +346,32 @@ def test_statistics(maskname):
     for key in ('sum', 'sumsq', 'mean', 'sigma', 'rms'):
         assert np.isclose(got[key], float(want[key]), rtol=RTOL), (key, got[key], want[key])
     assert not hasattr(gpu_cube(data, G.ADV_WCS, use_dask=False), 'statistics')      # the dask class only
+
+
+# ---- the opt-in tiled direct 2-D kernel (SC_DIRECT2D=1) ------------------------------------------------------------
+@pytest.mark.skipif(__import__('os').environ.get('SC_TEST_OPT_IN') != '1',
+                    reason="direct2d_tiled_kernel is opt-in and has not met hardware yet: set SC_TEST_OPT_IN=1 "
+                           "(tools/gpu_first_call.sh does)")
+@pytest.mark.parametrize('shape,kshape', [((2, 70, 40), (5, 7)), ((1, 30, 33), (9, 3)), ((3, 130, 97), (21, 21)),
+                                          ((1, 64, 64), (45, 45))])
+def test_tiled_direct_kernel_equals_the_direct_kernel(shape, kshape, monkeypatch):
+    S = scb()
+    rng = np.random.default_rng(kshape[0])
+    data = _random_cube(shape, seed=4, nan_frac=0.05)
+    data[:, 3:3 + kshape[0] + 4, 5:5 + kshape[1] + 6] = np.nan        # windows with nothing valid
+    if kshape[0] == kshape[1]:
+        sigma = kshape[0] / 16.0
+        kernel = S.EllipticalGaussian2DKernel(sigma, 0.6 * sigma, 0.7, x_size=kshape[1], y_size=kshape[0]).array
+    else:
+        kernel = rng.random(kshape) + 0.01                            # asymmetric: a missing flip would show
+    assert S.BaseSpectralCube._separable_factors(kernel) is None
+    sc, oc = gpu_cube(data, G.ADV_WCS, use_dask=True), oracle_cube(data, G.ADV_WCS, use_dask=True)
+    sc, oc = sc.with_mask(sc > -1.5), oc.with_mask(oc > -1.5)
+    monkeypatch.setenv('SC_DIRECT2D', '0')
+    direct = sc.spatial_smooth(S.CustomKernel(kernel)).unmasked_data[:]
+    monkeypatch.setenv('SC_DIRECT2D', '1')
+    tiled = sc.spatial_smooth(S.CustomKernel(kernel)).unmasked_data[:]
+    assert np.isnan(direct).any()
+    assert_maps_close(tiled, direct, rtol=2e-6, atol=1e-7, what='tiled vs direct %r' % (kshape,))
+    want = oc.spatial_smooth(oconv.Kernel(kernel))._data
+    assert_maps_close(tiled, want, rtol=RTOL, atol=1e-6, what='tiled vs oracle %r' % (kshape,))
