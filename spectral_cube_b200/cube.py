@@ -139,6 +139,11 @@ class BaseSpectralCube(object):
             raise ValueError("data should be a 3-d array")
         if t.stride(2) != 1:
             t = t.contiguous()
+        # a length-1 axis may carry any stride (numpy's `a[None]` gives 0): give it the one the kernels expect
+        sy = t.stride(1) if t.shape[1] > 1 and t.stride(1) >= t.shape[2] else t.shape[2]
+        sc = t.stride(0) if t.shape[0] > 1 and t.stride(0) >= t.shape[1] * sy else t.shape[1] * sy
+        if (t.shape[1] == 1 and t.stride(1) != sy) or (t.shape[0] == 1 and t.stride(0) != sc):
+            t = t.as_strided(tuple(t.shape), (sc, sy, 1), t.storage_offset())
         self._data_t = t
         self._hi = None                 # float64 tensor when the numpy-class semantics produce one ...
         self._hi_is_widened_f32 = False # ... or a flag: the float64 the reference returns is the float32 copy widened

@@ -94,6 +94,58 @@ class LowerDimensionalObject(np.ndarray):
 class Projection(LowerDimensionalObject):
     """2-D result (moment maps).  lower_dimensional_structures.py:246-292."""
 
+    @property
+    def beam(self):
+        """The beam in ``meta['beam']`` or the header's BMAJ/BMIN/BPA (lower_dimensional_structures.py:285-290);
+        AttributeError when there is none, so that ``hasattr(proj, 'beam')`` works as in the reference."""
+        from .beam import Beam
+        bm = self._meta.get('beam') if self._meta else None
+        if bm is None and self._header and 'BMAJ' in self._header:
+            try:
+                bm = Beam.from_fits_header(self._header)
+            except Exception:
+                bm = None
+        if bm is None:
+            raise AttributeError("this Projection has no beam")
+        return Beam.coerce(bm)
+
+    def convolve_to(self, beam, convolve=None, **kwargs):
+        """Convolve the image to a specified beam (lower_dimensional_structures.py:450-494): the map goes to the
+        device as a one-channel cube and through the same kernels as ``SpectralCube.convolve_to``.  No Jy/beam
+        rescale here (the reference's has none); ``convolve`` defaults to ``convolve_fft`` like the reference's."""
+        import warnings
+        from . import _lib
+        from .beam import Beam
+        from .cube import BaseSpectralCube
+        from .wcs import CelestialWCS, CubeWCS
+        if not isinstance(self._wcs, CelestialWCS):
+            raise ValueError("WCS does not contain two spatial axes.")          # utils.WCSCelestialError
+        if not hasattr(self, 'beam'):
+            raise ValueError("No beam is contained in Projection.meta.")
+        BaseSpectralCube._check_convolve_kwargs(kwargs)
+        beam = Beam.coerce(beam)
+        if beam == self.beam:
+            warnings.warn("The given beam is identical to the current beam. "
+                          "Skipping convolution.")
+            return self
+        m = np.asarray(self._wcs.cdelt, dtype=np.float64)[:, None] * np.asarray(self._wcs.pc, dtype=np.float64)
+        pixscale = float(np.sqrt(abs(m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0])))
+        kernel = beam.deconvolve(self.beam).as_kernel(pixscale)
+        fft = BaseSpectralCube._fft_semantics(convolve, default=True)
+        image = np.empty((1,) + self.shape, dtype=np.float32)             # a fresh block: proper strides for the size-1 axis
+        image[0] = self.value
+        plane = BaseSpectralCube(image,
+                                 CubeWCS(['RA---TAN', 'DEC--TAN', 'VRAD'], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [-1.0, 1.0, 1.0]))
+        out = plane._run_spatial_smooth(plane._kernel_array(kernel, 2), _lib.F32, passthrough=0, every_tap=True,
+                                        strategy_counts=plane._convolved_denominator_counts())
+        plane._convolve_epilogue(out, 1.0, fft)
+        meta = dict(self._meta)
+        meta['beam'] = beam
+        header = dict(self._header or {})
+        header.update(beam.to_header_keywords())
+        return Projection(out[0].cpu().numpy().astype(np.float64), unit=self._unit, wcs=self._wcs, meta=meta,
+                          header=header, copy=False)
+
     def __new__(cls, value, unit=None, wcs=None, meta=None, header=None, copy=True):
         if np.ndim(value) != 2:  # noqa
             raise ValueError("value should be a 2-d array")

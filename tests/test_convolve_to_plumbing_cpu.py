@@ -116,3 +116,27 @@ def test_varying_resolution_cube_reaches_the_library(host, use_dask):
         rot.convolve_to(S.Beam.from_arcsec(0.5))
     assert any(issubclass(x.category, S.BeamWarning) for x in w)
     assert abs(rot._pixscale_deg() - abs(G.ADV_WCS['cdelt'][1])) < 1e-15
+
+
+def test_projection_convolve_to_reaches_the_library(host):
+    """lower_dimensional_structures.py:450-494"""
+    S, calls = host
+    rng = np.random.default_rng(2)
+    cube = make(S, rng.normal(size=(6, 24, 32)), False, S.Beam.from_arcsec(3.0, 2.0, 60.0), 'Jy/beam')
+    m0 = cube.moment0()
+    assert m0.beam == cube.beam and hasattr(m0, 'beam')
+    del calls[:]
+    out = m0.convolve_to(S.Beam.from_arcsec(7.0, 4.0, 25.0))
+    assert len(calls) == 2 and isinstance(out, S.Projection) and out.shape == m0.shape and out.dtype == np.float64
+    assert out.beam == S.Beam.from_arcsec(7.0, 4.0, 25.0) and out.unit == m0.unit and out.wcs is m0.wcs
+    assert out.header['BMAJ'] == out.beam.major and m0.beam == cube.beam
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        assert m0.convolve_to(m0.beam) is m0
+    assert any("identical to the current beam" in str(x.message) for x in w)
+    nobeam = make(S, rng.normal(size=(6, 24, 32)), False).moment0()
+    assert not hasattr(nobeam, 'beam')
+    with pytest.raises(ValueError, match="No beam is contained in Projection.meta."):
+        nobeam.convolve_to(S.Beam.from_arcsec(7.0))
+    with pytest.raises(ValueError, match="two spatial axes"):
+        cube.moment(order=0, axis=1).convolve_to(S.Beam.from_arcsec(7.0))

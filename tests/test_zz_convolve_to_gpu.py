@@ -348,6 +348,27 @@ def test_statistics(maskname):
     assert not hasattr(gpu_cube(data, G.ADV_WCS, use_dask=False), 'statistics')      # the dask class only
 
 
+# ---- Projection.convolve_to (lower_dimensional_structures.py:450-494) ------------------------------------------
+def test_projection_convolve_to():
+    data = _random_cube((6, 40, 48), seed=12, nan_frac=0.02)
+    S = scb()
+    sc, oc = pair(data, False, beam=(3.0, 2.0, 60.0), unit='Jy/beam')
+    m0 = sc.moment0()
+    assert m0.beam == sc.beam
+    target = S.Beam.from_arcsec(7.0, 4.0, 25.0)
+    got = m0.convolve_to(target)
+    kernel = OBeam.arcsec(7.0, 4.0, 25.0).deconvolve(OBeam.arcsec(3.0, 2.0, 60.0)).as_kernel(oc._pixscale())
+    image = np.asarray(m0.value, dtype=np.float64)
+    scale = float(np.nanmax(np.abs(image)))
+    assert_maps_close(got.value, oconv.convolve_fft(image, kernel), rtol=RTOL, atol=1e-6 * scale, what='convolve_fft')
+    direct = m0.convolve_to(target, convolve=_named('convolve'))
+    assert_maps_close(direct.value, oconv.convolve(image, kernel), rtol=RTOL, atol=1e-6 * scale, what='convolve')
+    assert isinstance(got, S.Projection) and got.value.dtype == np.float64 and got.unit == m0.unit       # no Jy/beam rescale
+    assert got.beam == target and got.header['BMAJ'] == target.major and got.wcs is m0.wcs
+    with pytest.raises(ValueError, match="No beam is contained in Projection.meta."):
+        gpu_cube(data, G.ADV_WCS).moment0().convolve_to(target)
+
+
 # ---- the opt-in tiled direct 2-D kernel (SC_DIRECT2D=1) ------------------------------------------------------------
 @pytest.mark.skipif(__import__('os').environ.get('SC_TEST_OPT_IN') != '1',
                     reason="direct2d_tiled_kernel is opt-in and has not met hardware yet: set SC_TEST_OPT_IN=1 "

@@ -129,6 +129,14 @@ class FakeLib(object):
         view(out, np.uint8, shape, (ny * nx, nx, 1))[...] = include(mask, data, shape)
         return 0
 
+    def sc_moments_axis0(self, cube, nchan, ny, nx, sc, sy, mask, offsets, pix_size, world0, want_bits, o0, o1, o2, ws, wsb, stream):
+        assert want_bits == 1, "only moment 0 is emulated"
+        shape = (nchan, ny, nx)
+        data = view(cube, np.float32, shape, (sc, sy, 1))
+        f = np.where(include(mask, data, shape) & ~np.isnan(data), data, 0.0).astype(np.float64)
+        view(o0, np.float64, (ny, nx), (nx, 1))[...] = f.sum(axis=0) * pix_size
+        return 0
+
     def sc_reduce_axis0(self, cube, nchan, ny, nx, sc, sy, mask, osum, ocnt, om2, omin, omax, oamin, oamax, stream):
         import warnings
         shape = (nchan, ny, nx)
