@@ -214,14 +214,31 @@ class RowShardedCube(object):
     def spectral_interpolate(self, grid, **kw):
         return self._wrap(self.local.spectral_interpolate(grid, **kw))
 
-    # ---- spatial_smooth: halo rows from the two neighbours ---------------------------------------------
-    def spatial_smooth(self, kernel, halo_mode='p2p', **kw):
+    # ---- spatial_smooth / convolve_to: halo rows from the two neighbours ------------------------------------
+    def _is_sharded(self):
+        dist = _dist()
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _blank_planes(self):
+        """Device uint8 (nchan): 1 where the mask includes nothing of the WHOLE image plane (all shards) -- the test
+        of the numpy class's `_apply_spatial_function` (spectral_cube.py:161-172).  None without a mask."""
+        import torch
+        loc = self.local
+        if loc._mask is None:
+            return None
+        inc = loc._mask._include_tensor(loc._data)
+        blank = (~inc.reshape(inc.shape[0], -1).any(dim=1)).to(torch.int32)
+        if self._is_sharded():
+            _dist().all_reduce(blank, op=_dist().ReduceOp.MIN, group=self.group)
+        return blank.to(torch.uint8)
+
+    def _smooth_rows(self, k2d, halo_mode='p2p', counts=None, every_tap=False, need_blank=False):
+        """The spatial kernels on this rank's rows with the neighbours' filled edge rows as halos.
+        Returns (float32 result, job-wide blank-plane flags or None)."""
         import torch
         from . import _lib
         lib = _lib.load()
         loc = self.local
-        loc.check_jybeam_smoothing(raise_error_jybm=kw.pop('raise_error_jybm', True))
-        k2d = loc._kernel_array(kernel, 2)
         h = k2d.shape[0] // 2
         nchan, ny, nx = loc.shape
         if h > ny:
@@ -236,33 +253,64 @@ class RowShardedCube(object):
                                                float(loc._fill_value), row0, h, out.data_ptr(), stream))
             return out
         halo_top = halo_bot = None
-        if h > 0:
-            halo_top, halo_bot = exchange_halo_rows(pack(0), pack(ny - h), self.group, mode=halo_mode)
         dask = loc._mirrors_dask
-        # one denominator strategy for the whole job (bit-identical with the unsharded result): the ranks'
-        # sample counts are summed (8 bytes; the only other exchange of this op are the halo rows)
-        counts = loc._spatial_strategy_counts()
-        dist = _dist()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        sharded = self._is_sharded()
+        if h > 0 and sharded:
+            halo_top, halo_bot = exchange_halo_rows(pack(0), pack(ny - h), self.group, mode=halo_mode)
+        if counts is None:
+            # one denominator strategy for the whole job (bit-identical with the unsharded result): the ranks'
+            # sample counts are summed (8 bytes; the only other exchange of this op are the halo rows)
+            counts = loc._spatial_strategy_counts()
+            if sharded:
+                _dist().all_reduce(counts, op=_dist().ReduceOp.SUM, group=self.group)
         # numpy class: `_apply_spatial_function` copies a channel image through when the mask includes nothing of
         # the WHOLE image (spectral_cube.py:161-172).  A shard cannot take that decision on its own rows -- a plane
         # blank here may have data next door that reaches across the boundary through the halo rows -- so shards
         # always convolve.  A plane blank everywhere convolves to what the copy would give for the usual fill values
         # (NaN stays NaN, 0 stays 0); for any other finite fill the job-wide blank planes are copied afterwards.
-        sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
         passthrough = 0 if (sharded and not dask) else None
         out = loc._run_spatial_smooth(k2d, _lib.F32, halo_top=halo_top, halo_bot=halo_bot, halo_rows=h,
-                                      strategy_counts=counts, passthrough=passthrough)
+                                      strategy_counts=counts, passthrough=passthrough, every_tap=every_tap)
         fill = float(loc._fill_value)
-        if sharded and not dask and loc._mask is not None and np.isfinite(fill) and fill != 0.0:
-            inc = loc._mask._include_tensor(src)
-            blank = (~inc.reshape(nchan, -1).any(dim=1)).to(torch.int32)
-            dist.all_reduce(blank, op=dist.ReduceOp.MIN, group=self.group)
-            blank = blank.bool()
-            if bool(blank.any()):
-                out[blank] = loc._filled_tensor(fill)[blank]
-        new = loc._new_cube_with(data=out) if dask else loc._new_cube_reporting_f64(out)
+        blank = None
+        if not dask:
+            if not sharded:
+                blank = loc._passthrough_flags                      # what the library found for this (whole) image
+            elif need_blank or (np.isfinite(fill) and fill != 0.0):
+                blank = self._blank_planes()
+                if blank is not None and np.isfinite(fill) and fill != 0.0 and bool(blank.any()):
+                    out[blank.bool()] = loc._filled_tensor(fill)[blank.bool()]
+        return out, blank
+
+    def spatial_smooth(self, kernel, halo_mode='p2p', **kw):
+        loc = self.local
+        loc.check_jybeam_smoothing(raise_error_jybm=kw.pop('raise_error_jybm', True))
+        out, _ = self._smooth_rows(loc._kernel_array(kernel, 2), halo_mode=halo_mode)
+        new = loc._new_cube_with(data=out) if loc._mirrors_dask else loc._new_cube_reporting_f64(out)
+        return self._wrap(new)
+
+    def convolve_to(self, beam, convolve=None, halo_mode='p2p', **kw):
+        """``SpectralCube.convolve_to`` on a row-sharded cube (spectral_cube.py:3335-3392; dask :1412-1464): the
+        deconvolved beam's kernel through the halo-exchanging spatial kernels, then the in-place epilogue (Jy/beam
+        rescale, ``convolve_fft``'s zero for empty windows) on this rank's rows -- no other communication."""
+        import warnings
+        from .beam import Beam
+        loc = self.local
+        loc._check_convolve_kwargs(kw)
+        beam = Beam.coerce(beam)
+        if beam == loc.beam:
+            warnings.warn("The given beam is identical to the current beam. "
+                          "Skipping convolution.")
+            return self
+        kernel = beam.deconvolve(loc.beam).as_kernel(loc._pixscale_deg())
+        factor = beam.sr / loc.beam.sr if loc._is_jybeam() else 1.0
+        fft = loc._fft_semantics(convolve, default=not loc._mirrors_dask)
+        out, blank = self._smooth_rows(loc._kernel_array(kernel, 2), halo_mode=halo_mode, every_tap=True,
+                                       counts=loc._convolved_denominator_counts(),
+                                       need_blank=(factor != 1.0 or fft))
+        loc._convolve_epilogue(out, factor, fft, skip=blank)
+        new = loc._new_cube_with(data=out) if loc._mirrors_dask else loc._new_cube_reporting_f64(out)
+        new._attach_beam(beam)
         return self._wrap(new)
 
     # ---- reproject: one re-shard to channels, then whole planes locally -------------------------------

@@ -140,3 +140,27 @@ def test_projection_convolve_to_reaches_the_library(host):
         nobeam.convolve_to(S.Beam.from_arcsec(7.0))
     with pytest.raises(ValueError, match="two spatial axes"):
         cube.moment(order=0, axis=1).convolve_to(S.Beam.from_arcsec(7.0))
+
+
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_row_sharded_convolve_to_reaches_the_library(host, use_dask):
+    """One process (no process group): the sharded wrapper degenerates to the whole image; the exchange functions
+    themselves are covered by the gloo tests in tests/test_distributed_cpu.py."""
+    S, calls = host
+    from spectral_cube_b200 import distributed as D
+    rng = np.random.default_rng(3)
+    cube = make(S, rng.normal(size=(3, 40, 64)), use_dask, S.Beam.from_arcsec(3.0), 'Jy/beam')
+    cube = cube.with_mask(cube > -10.0)
+    sh = D.RowShardedCube(cube, 40, 0)
+    del calls[:]
+    out = sh.convolve_to(S.Beam.from_arcsec(5.0))
+    # one smoothing call and the epilogue (no neighbours: no halo rows packed)
+    assert len(calls) == 2 and isinstance(out, D.RowShardedCube) and out.local.beam == S.Beam.from_arcsec(5.0)
+    assert type(out.local) is type(cube) and out.shape == (3, 40, 64)
+    del calls[:]
+    sm = sh.spatial_smooth(S.Gaussian2DKernel(1.0), raise_error_jybm=False)
+    assert len(calls) == 2 and sm.local.beam == cube.beam            # the strategy sample + the smoothing call
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        assert sh.convolve_to(cube.beam) is sh
+    assert w

@@ -1,7 +1,8 @@
 """
 Host-side logic of the multi-GPU path on CPU: world_size-2 and -3 `gloo` process groups exercise
 the row partition, the halo exchange (neighbour send/recv and the all-gather variant), the
-rows<->channels re-shard and the gather of row-sharded maps.  No GPU, no CUDA library calls.
+rows<->channels re-shard and the gather of row-sharded maps; the last test also drives the row-sharded
+spatial_smooth / convolve_to wrappers into the real library (calls stop at the missing device).  No GPU.
 """
 import os
 import socket
@@ -123,3 +124,52 @@ def _gather_job(rank, world):
 @pytest.mark.parametrize('world', [2, 3])
 def test_gather_rows(world):
     assert all(run_group(world, _gather_job))
+
+
+def _sharded_smoothing_job(rank, world):
+    """Row-sharded spatial_smooth / convolve_to host logic under gloo: tensors stay on the host, the real library is
+    called and stops at its first CUDA call (tolerated here only, like the `host` fixture of conftest.py); the halo
+    exchange, the job-wide blank-plane all-reduce and the strategy-count all-reduce run for real."""
+    import spectral_cube_b200 as S
+    from spectral_cube_b200 import cube as C, _lib
+    from spectral_cube_b200.masks import LazyMask
+
+    class _Stream(object):
+        cuda_stream = 0
+
+    calls = []
+
+    def check(rc):
+        msg = _lib.load().sc_last_error().decode() if rc else ''
+        calls.append(rc)
+        if rc and 'CUDA error' not in msg and 'not available from the driver' not in msg:
+            raise AssertionError("the library refused the arguments: %d %s" % (rc, msg))
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    _lib.require_cuda = lambda: torch
+    _lib.check = check
+    C._stream = lambda: 0
+    wcs = S.CubeWCS(ctype=['RA---SIN', 'DEC--SIN', 'VOPT'], crval=[23.0, 30.0, -321.0], crpix=[20.0, 30.0, 1.0],
+                    cdelt=[-5.55555561268e-4, 5.55555561268e-4, 1.288], cunit=['deg', 'deg', 'km/s'])
+    ny = 60
+    y0, y1 = D.row_partition(ny, world)[rank]
+    rng = np.random.default_rng(rank)
+    ok = True
+    for cls in (S.SpectralCube, S.DaskSpectralCube):
+        for fill in (np.nan, 5.0):
+            sh = D.RowShardedCube.from_full_wcs(cls, rng.normal(size=(3, y1 - y0, 64)).astype(np.float32), wcs, ny,
+                                                unit='Jy/beam', beam=S.Beam.from_arcsec(3.0), fill_value=fill)
+            sh.local._mask = LazyMask(np.isfinite, cube=sh.local)
+            sh = sh.with_mask(sh > -10.0)
+            out = sh.convolve_to(S.Beam.from_arcsec(5.0))
+            ok &= out.local.beam == S.Beam.from_arcsec(5.0) and out.local.shape == sh.local.shape
+            ok &= type(out.local) is cls and out.y0 == y0
+            sm = sh.spatial_smooth(S.Gaussian2DKernel(1.0), raise_error_jybm=False, halo_mode='allgather')
+            ok &= sm.local.beam == sh.local.beam
+    return bool(ok) and len(calls) > 8
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_row_sharded_smoothing_host_logic(world):
+    assert all(run_group(world, _sharded_smoothing_job))
