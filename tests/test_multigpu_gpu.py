@@ -67,6 +67,16 @@ def _worker(rank, world, port, q):
         for mode in ('p2p', 'allgather'):
             got = shard.spatial_smooth(k, halo_mode=mode).local._data
             res['spatial_' + mode] = bool(torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref[:, y0:y1], nan=-7.0)))
+        # convolve_to on row shards: both classes, Jy/beam rescale and the convolve_fft rule included
+        pix = float(abs(wcs.cdelt[1]))
+        for cls in (scb.SpectralCube, scb.DaskSpectralCube):
+            w2 = with_isfinite(cls(full, wcs, unit='Jy/beam', beam=scb.Beam(3 * pix)))
+            s2 = D.RowShardedCube.from_full_wcs(cls, local, wcs, ny, unit='Jy/beam', beam=scb.Beam(3 * pix))
+            with_isfinite(s2.local)
+            ref = w2.convolve_to(scb.Beam(5 * pix))._data
+            got = s2.convolve_to(scb.Beam(5 * pix)).local._data
+            res['convolve_to_' + cls.__name__] = bool(torch.equal(torch.nan_to_num(got, nan=-7.0),
+                                                                  torch.nan_to_num(ref[:, y0:y1], nan=-7.0)))
         # reproject through the row->channel re-shard
         a = np.radians(30.0)
         hdr = dict(whole.header)
