@@ -848,6 +848,33 @@ plane_none_included_kernel(const __grid_constant__ SpatialParams p, uint8_t *fla
     if (threadIdx.x == 0) flags[c] = found ? 0 : 1;
 }
 
+// direct2d_kernel, or the opt-in tiled kernel (SC_DIRECT2D=1) when the taps fit and none is negative (the tiled
+// kernel's "nothing valid" test is a float32 sum of non-negative terms)
+static int launch_direct2d(const DirectParams &d, int out_dtype, bool nonneg, cudaStream_t s) {
+    const SpatialParams &p = d.sp;
+    const int nt = d.nty * d.ntx;
+    if (env_int("SC_DIRECT2D", 0) == 1 && nt <= DT_MAX_TAPS && nonneg) {
+        const int64_t tiles_x = cdiv(p.nx, DT_TX), tiles_y = cdiv(p.ny, DT_TY);
+        const int64_t grid = tiles_x * tiles_y * p.nchan;
+        SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
+        const size_t box = (size_t)(DT_TX + d.ntx - 1) * (DT_TY + d.nty - 1 + DT_RY);
+        const size_t smem = (size_t)((nt + 1) & ~1) * 8 + box * 12;
+        if (out_dtype == SC_F64) {
+            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            direct2d_tiled_kernel<1><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
+        } else {
+            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            direct2d_tiled_kernel<0><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
+        }
+    } else {
+        const int64_t total = p.nchan * p.ny * p.nx;
+        if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+        else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
+    }
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+}
+
 static int maybe_passthrough_flags(SpatialParams &p, int plane_passthrough, void *workspace, size_t workspace_bytes,
                                    size_t offset, cudaStream_t s) {
     p.passthrough = nullptr;
@@ -1088,18 +1115,18 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
     }
     SC_CHECK_ARG(nt <= 6000, "kernel too large for the direct path (%d taps)", nt);
     double *host = (double *)malloc((size_t)nt * 8);
-    for (int a = 0; a < ntaps_y; ++a) for (int b = 0; b < ntaps_x; ++b) host[a * ntaps_x + b] = (taps_y[a] / sy) * (taps_x[b] / sx);
+    bool all_nonneg = true;
+    for (int a = 0; a < ntaps_y; ++a) for (int b = 0; b < ntaps_x; ++b) {
+        host[a * ntaps_x + b] = (taps_y[a] / sy) * (taps_x[b] / sx);
+        all_nonneg = all_nonneg && host[a * ntaps_x + b] >= 0.0;
+    }
     double *tdev = (double *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     cudaError_t ce = cudaMemcpyAsync(tdev, host, (size_t)nt * 8, cudaMemcpyHostToDevice, s);
     free(host);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(taps)");
     DirectParams d{p, tdev, ntaps_y, ntaps_x};
-    const int64_t total = nchan * ny * nx;
     LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
-    if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
-    else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
-    SC_CUDA(cudaGetLastError());
-    return SC_OK;
+    return launch_direct2d(d, out_dtype, all_nonneg, s);
 }
 
 extern "C" int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
@@ -1138,28 +1165,8 @@ extern "C" int sc_spatial_smooth_2d(const float *in, void *out, int out_dtype,
     free(host);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(taps)");
     DirectParams d{p, tdev, ntaps_y, ntaps_x};
-    const int64_t total = nchan * ny * nx;
     LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
-    bool nonneg = true;                                  // the float32 zero test of the tiled kernel's denominator
+    bool nonneg = true;
     for (int i = 0; i < nt; ++i) nonneg = nonneg && taps[i] / sum >= 0.0;
-    if (env_int("SC_DIRECT2D", 0) == 1 && nt <= DT_MAX_TAPS && nonneg) {
-        const int64_t tiles_x = cdiv(nx, DT_TX), tiles_y = cdiv(ny, DT_TY);
-        const int64_t grid = tiles_x * tiles_y * nchan;
-        SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
-        const size_t box = (size_t)(DT_TX + ntaps_x - 1) * (DT_TY + ntaps_y - 1 + DT_RY);
-        const size_t smem = (size_t)((nt + 1) & ~1) * 8 + box * 12;
-        if (out_dtype == SC_F64) {
-            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            direct2d_tiled_kernel<1><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
-        } else {
-            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            direct2d_tiled_kernel<0><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
-        }
-        SC_CUDA(cudaGetLastError());
-        return SC_OK;
-    }
-    if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
-    else                     direct2d_kernel<0><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);
-    SC_CUDA(cudaGetLastError());
-    return SC_OK;
+    return launch_direct2d(d, out_dtype, nonneg, s);
 }
