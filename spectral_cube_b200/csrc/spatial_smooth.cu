@@ -728,12 +728,16 @@ direct2d_kernel(const __grid_constant__ DirectParams d) {
 // Each thread keeps 8 float64 numerators: for every kernel column it walks the kernel rows with a 16-deep
 // register window of its image column (1 LDS.64 + 1 LDS.32 + 1 broadcast tap per 8 DFMA + 8 FFMA); the
 // denominator is summed in float32 per kernel column and carried in float64 across columns.
-constexpr int DT_TX = 32, DT_TY = 64, DT_RY = 8;
-constexpr int DT_MAX_TAPS = 2048;                 // 45 x 45: taps + box fit the 227 KB of shared memory
+constexpr int DT_TX = 32, DT_RY = 8;
+constexpr size_t DT_MAX_SMEM = 200 * 1024;        // taps + box have to fit (227 KB per CTA on sm_100)
 
-template <int OUT64>
-__global__ void __launch_bounds__(256)
+// NW warps per CTA: the tile is 32 columns x 8 NW rows (8 warps for the usual kernels, 4 when the box of a wide
+// kernel would not fit otherwise)
+template <int OUT64, int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 4 ? 1 : 2)
 direct2d_tiled_kernel(const __grid_constant__ DirectParams d, int tiles_x, int tiles_y) {
+    constexpr int DT_TY = NW * DT_RY;
+    constexpr int NTHREADS = 32 * NW;
     const SpatialParams &p = d.sp;
     extern __shared__ __align__(16) unsigned char dt_smem[];
     const int nty = d.nty, ntx = d.ntx, hy = nty >> 1, hx = ntx >> 1;
@@ -749,8 +753,8 @@ direct2d_tiled_kernel(const __grid_constant__ DirectParams d, int tiles_x, int t
     const int64_t c = b / tiles_y;
     const int64_t x0 = tx_i * DT_TX, y0 = ty_i * DT_TY;
 
-    for (int i = tid; i < nty * ntx; i += 256) staps[i] = d.taps[i];
-    for (int i = tid; i < bw * bh; i += 256) {
+    for (int i = tid; i < nty * ntx; i += NTHREADS) staps[i] = d.taps[i];
+    for (int i = tid; i < bw * bh; i += NTHREADS) {
         const int q = i / bw, pcol = i - q * bw;
         const int64_t yy = y0 - hy + q, xx = x0 - hx + pcol;
         float v = 0.0f;                                // zero padding: a valid sample
@@ -848,24 +852,26 @@ plane_none_included_kernel(const __grid_constant__ SpatialParams p, uint8_t *fla
     if (threadIdx.x == 0) flags[c] = found ? 0 : 1;
 }
 
-// direct2d_kernel, or the opt-in tiled kernel (SC_DIRECT2D=1) when the taps fit and none is negative (the tiled
+// direct2d_kernel, or the opt-in tiled kernel (SC_DIRECT2D=1) when taps + box fit shared memory and no tap is negative (the tiled
 // kernel's "nothing valid" test is a float32 sum of non-negative terms)
 static int launch_direct2d(const DirectParams &d, int out_dtype, bool nonneg, cudaStream_t s) {
     const SpatialParams &p = d.sp;
     const int nt = d.nty * d.ntx;
-    if (env_int("SC_DIRECT2D", 0) == 1 && nt <= DT_MAX_TAPS && nonneg) {
-        const int64_t tiles_x = cdiv(p.nx, DT_TX), tiles_y = cdiv(p.ny, DT_TY);
+    const size_t taps_bytes = (size_t)((nt + 1) & ~1) * 8;
+    const size_t smem8 = taps_bytes + (size_t)(DT_TX + d.ntx - 1) * (8 * DT_RY + d.nty - 1 + DT_RY) * 12;
+    const size_t smem4 = taps_bytes + (size_t)(DT_TX + d.ntx - 1) * (4 * DT_RY + d.nty - 1 + DT_RY) * 12;
+    if (env_int("SC_DIRECT2D", 0) == 1 && nonneg && smem4 <= DT_MAX_SMEM) {
+        const int nw = smem8 <= DT_MAX_SMEM ? 8 : 4;
+        const size_t smem = nw == 8 ? smem8 : smem4;
+        const int64_t tiles_x = cdiv(p.nx, DT_TX), tiles_y = cdiv(p.ny, nw * DT_RY);
         const int64_t grid = tiles_x * tiles_y * p.nchan;
         SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
-        const size_t box = (size_t)(DT_TX + d.ntx - 1) * (DT_TY + d.nty - 1 + DT_RY);
-        const size_t smem = (size_t)((nt + 1) & ~1) * 8 + box * 12;
-        if (out_dtype == SC_F64) {
-            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            direct2d_tiled_kernel<1><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
-        } else {
-            SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            direct2d_tiled_kernel<0><<<(unsigned)grid, 256, smem, s>>>(d, (int)tiles_x, (int)tiles_y);
-        }
+#define SC_LAUNCH_TILED(O64, NWARPS) do { \
+        SC_CUDA(cudaFuncSetAttribute(direct2d_tiled_kernel<O64, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        direct2d_tiled_kernel<O64, NWARPS><<<(unsigned)grid, 32 * NWARPS, smem, s>>>(d, (int)tiles_x, (int)tiles_y); } while (0)
+        if (out_dtype == SC_F64) { if (nw == 8) SC_LAUNCH_TILED(1, 8); else SC_LAUNCH_TILED(1, 4); }
+        else                     { if (nw == 8) SC_LAUNCH_TILED(0, 8); else SC_LAUNCH_TILED(0, 4); }
+#undef SC_LAUNCH_TILED
     } else {
         const int64_t total = p.nchan * p.ny * p.nx;
         if (out_dtype == SC_F64) direct2d_kernel<1><<<(unsigned)cdiv(total, 256), 256, (size_t)nt * 8, s>>>(d);

@@ -77,8 +77,8 @@ def test_projection_container():
         Projection(np.zeros(3))
 
 
-@pytest.mark.parametrize('shape,kshape', [((70, 40), (5, 7)), ((20, 20), (17, 11))])
-def test_model_of_the_tiled_direct_kernel_matches_the_oracle(shape, kshape):
+@pytest.mark.parametrize('shape,kshape,nw', [((70, 40), (5, 7), 8), ((20, 20), (17, 11), 8), ((45, 33), (9, 5), 4)])
+def test_model_of_the_tiled_direct_kernel_matches_the_oracle(shape, kshape, nw):
     """direct2d_tiled_kernel (opt-in, csrc/spatial_smooth.cu) restated thread by thread in Python: its box staging,
     register-window walk and kernel flip give astropy's convolution (asymmetric random kernel, NaN holes)."""
     from tools.dryrun.model_direct2d_tiled import tiled
@@ -88,7 +88,7 @@ def test_model_of_the_tiled_direct_kernel_matches_the_oracle(shape, kshape):
     img[3:3 + kshape[0] + 4, 5:5 + kshape[1] + 6] = np.nan
     kernel = rng.random(kshape) + 0.01
     want = oconv.convolve(img.astype(np.float64), kernel, normalize_kernel=True)
-    got = tiled(img, kernel)
+    got = tiled(img, kernel, nw=nw)
     assert np.isnan(want).any() and np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     np.testing.assert_allclose(got[ok], want[ok], rtol=1e-6, atol=1e-7)

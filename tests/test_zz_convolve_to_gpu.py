@@ -374,7 +374,8 @@ def test_projection_convolve_to():
                     reason="direct2d_tiled_kernel is opt-in and has not met hardware yet: set SC_TEST_OPT_IN=1 "
                            "(tools/gpu_first_call.sh does)")
 @pytest.mark.parametrize('shape,kshape', [((2, 70, 40), (5, 7)), ((1, 30, 33), (9, 3)), ((3, 130, 97), (21, 21)),
-                                          ((1, 64, 64), (45, 45))])
+                                          ((1, 64, 64), (45, 45)),
+                                          ((1, 80, 72), (77, 77))])            # 77 x 77: the 4-warp, 32-row tile
 def test_tiled_direct_kernel_equals_the_direct_kernel(shape, kshape, monkeypatch):
     S = scb()
     rng = np.random.default_rng(kshape[0])
@@ -392,7 +393,7 @@ def test_tiled_direct_kernel_equals_the_direct_kernel(shape, kshape, monkeypatch
     direct = sc.spatial_smooth(S.CustomKernel(kernel)).unmasked_data[:]
     monkeypatch.setenv('SC_DIRECT2D', '1')
     tiled = sc.spatial_smooth(S.CustomKernel(kernel)).unmasked_data[:]
-    assert np.isnan(direct).any()
+    assert np.isnan(direct).any() or kshape[0] > 45          # (the widest kernel reaches the zero padding from everywhere)
     assert_maps_close(tiled, direct, rtol=2e-6, atol=1e-7, what='tiled vs direct %r' % (kshape,))
     want = oc.spatial_smooth(oconv.Kernel(kernel))._data
     assert_maps_close(tiled, want, rtol=RTOL, atol=1e-6, what='tiled vs oracle %r' % (kshape,))

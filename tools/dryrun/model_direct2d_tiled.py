@@ -2,8 +2,12 @@
 index arithmetic, one Python iteration per CUDA thread.  TEST TOOLING: tests/test_host_logic.py checks it against the
 oracle convolution, which is how the kernel's indexing was verified before it could run on hardware."""
 import numpy as np
-TX, TY, RY = 32, 64, 8
-def tiled(img, K):
+TX, RY = 32, 8
+
+
+def tiled(img, K, nw=8):
+    """nw = warps per CTA (8 or 4): the tile is 32 columns x 8 nw rows."""
+    TY = nw * RY
     ny, nx = img.shape; nty, ntx = K.shape; hy, hx = nty >> 1, ntx >> 1
     Kn = K / K.sum()
     bw, bh = TX + ntx - 1, TY + nty - 1 + RY
@@ -20,7 +24,7 @@ def tiled(img, K):
                     v = img[yy, xx]
                 good = v == v
                 sval[i] = float(v) if good else 0.0; sok[i] = 1.0 if good else 0.0
-            for warp in range(8):
+            for warp in range(nw):
                 r0 = warp * RY
                 for lane in range(32):
                     top = np.zeros(RY); botd = np.zeros(RY)
