@@ -5,7 +5,7 @@ at its first CUDA API call ("no device"), which is tolerated here and only here 
 tests/conftest.py).  What this pins: class
 construction and beam propagation, the per-channel plan of VaryingResolutionSpectralCube, which C-ABI entry
 points a call reaches and in what number, and that the library accepts the shapes / strides / flags it is given.
-Numerical parity is the GPU tests' business (tests/test_zz_convolve_to_gpu.py).
+Numerical parity is the GPU tests' business (tests/test_convolve_to_gpu.py).
 """
 import warnings
 

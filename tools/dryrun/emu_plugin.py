@@ -1,14 +1,14 @@
 """
 Dry-run aid, TEST TOOLING ONLY (nothing in the product or in the default test runs imports it).
 
-`tests/test_zz_convolve_to_gpu.py` was written after the round's GPU budget was spent.  To check the TESTS --
+`tests/test_convolve_to_gpu.py` was written after the round's GPU budget was spent.  To check the TESTS --
 their expectations, tolerances, NaN patterns, the host plumbing up to the C ABI -- before their first run on
 hardware, this pytest plugin swaps `spectral_cube_b200._lib.load()` for a numpy emulation of the few entry points
 `convolve_to` / `statistics` reach, written from their documented semantics in include/sc_b200.h
 (sc_spatial_smooth_sep_ex, sc_spatial_smooth_2d, sc_scale, sc_fill_masked, sc_mask_include, sc_reduce_axis0 and the
 mask descriptor), keeps tensors on the host and un-skips the gpu-marked tests of the file it is pointed at:
 
-    PYTHONPATH=tools/dryrun python -m pytest -p emu_plugin tests/test_zz_convolve_to_gpu.py -q -p no:cacheprovider
+    PYTHONPATH=tools/dryrun python -m pytest -p emu_plugin tests/test_convolve_to_gpu.py -q -p no:cacheprovider
 
 A green run says the tests are self-consistent with the documented kernel semantics; it says NOTHING about the CUDA
 kernels.  It found three wrong expectations and one real host-side issue (the separability test for beam kernels).

@@ -1,6 +1,6 @@
 #!/bin/bash
-# First gpurun call of a round: everything that was written without a GPU gets its first run, the bench line and the
-# launch list are refreshed.  Usage (from the repo root, in the build container):
+# First gpurun call of a round: the whole GPU suite, the bench line, the launch list, and the timings round 1 could not
+# take any more (convolve_to and its kernels).  Usage (from the repo root, in the build container):
 #   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
 # Outputs land in gpurun_out/ (scratch); copy what should be judged into profiles/ with tools/ncu_summary.py.
 set -u
@@ -8,9 +8,6 @@ mkdir -p gpurun_out
 # 1. the whole GPU suite WITHOUT -x: one run shows every failure of the files that never met hardware
 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/tests.log 2>&1
 tail -15 gpurun_out/tests.log
-# 1b. opt-in kernels that have not met hardware yet (direct2d_tiled_kernel)
-SC_TEST_OPT_IN=1 python -m pytest tests/test_zz_convolve_to_gpu.py -m gpu -q -p no:cacheprovider -k tiled > gpurun_out/tests_opt_in.log 2>&1
-tail -5 gpurun_out/tests_opt_in.log
 # 2. the bench line (configs[1]) and the reference arm
 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 600 gpurun_out/bench_n1.json
