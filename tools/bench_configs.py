@@ -182,8 +182,22 @@ if 'convolve' in which and world == 1:
         c = scb.SpectralCube(dev, w, unit=unit, beam=scb.Beam(3 * pix, 2 * pix, 60.0))
         c._mask = scb.LazyMask(np.isfinite, cube=c)
         k = scb.Beam(5 * pix, 4 * pix, 25.0).deconvolve(c.beam).as_kernel(pix)
-        ms = timeit(lambda: c.convolve_to(scb.Beam(5 * pix, 4 * pix, 25.0)), n=2, warm=1)
-        emit('convolve', 'convolve_to, rotated elliptical beams (%dx%d taps, direct2d_kernel), unit %s' % (k.shape + (unit,)), V, ms, (8 + 8) * V)
+        for tiled in ('0', '1'):
+            os.environ['SC_DIRECT2D'] = tiled
+            ms = timeit(lambda: c.convolve_to(scb.Beam(5 * pix, 4 * pix, 25.0)), n=2, warm=1)
+            emit('convolve', 'convolve_to, rotated elliptical beams (%dx%d taps, %s), unit %s'
+                 % (k.shape + ('direct2d_tiled_kernel' if tiled == '1' else 'direct2d_kernel', unit)), V, ms, (8 + 8) * V)
+        os.environ.pop('SC_DIRECT2D', None)
+    # a round beam too wide for the separable kernels (half-width > 16): the outer product on the direct path
+    c = scb.SpectralCube(dev, w, unit='K', beam=scb.Beam(3 * pix))
+    c._mask = scb.LazyMask(np.isfinite, cube=c)
+    k = scb.Beam(8 * pix).deconvolve(c.beam).as_kernel(pix)
+    for tiled in ('0', '1'):
+        os.environ['SC_DIRECT2D'] = tiled
+        ms = timeit(lambda: c.convolve_to(scb.Beam(8 * pix)), n=1, warm=1)
+        emit('convolve', 'convolve_to, round 3 px -> 8 px beam (%dx%d outer product, %s)'
+             % (k.shape + ('direct2d_tiled_kernel' if tiled == '1' else 'direct2d_kernel',)), V, ms, (8 + 8) * V)
+    os.environ.pop('SC_DIRECT2D', None)
     rng = np.random.default_rng(0)
     beams = scb.Beams(major=rng.uniform(2.5, 3.5, nchan) * pix, minor=rng.uniform(2.0, 2.5, nchan) * pix, pa=rng.uniform(0, 180, nchan))
     vr = scb.VaryingResolutionSpectralCube(dev, w, unit='Jy/beam', beams=beams)
