@@ -290,6 +290,16 @@ class BaseSpectralCube(object):
     def with_fill_value(self, fill_value):
         return self._new_cube_with(fill_value=fill_value)
 
+    def mask_channels(self, goodchannels):
+        """Mask out whole channels with a 1-D boolean array (spectral_cube.py:3394-3418)."""
+        goodchannels = np.asarray(goodchannels, dtype='bool')
+        if goodchannels.ndim != 1:
+            raise ValueError("goodchannels mask must be one-dimensional")
+        if goodchannels.size != self.shape[0]:
+            raise ValueError("goodchannels must have a length equal to the "
+                             "cube's spectral dimension.")
+        return self.with_mask(goodchannels[:, None, None])
+
     def with_spectral_unit(self, unit, **kwargs):
         return self._new_cube_with(spectral_unit=unit)
 
@@ -1244,14 +1254,8 @@ class VaryingResolutionSpectralCube(BaseSpectralCube):
 
     def mask_channels(self, goodchannels):
         """:4270-4300 -- the beams of the masked channels are skipped by ``convolve_to``."""
-        goodchannels = np.asarray(goodchannels, dtype='bool')
-        if goodchannels.ndim != 1:
-            raise ValueError("goodchannels mask must be one-dimensional")
-        if goodchannels.size != self.shape[0]:
-            raise ValueError("goodchannels must have a length equal to the "
-                             "cube's spectral dimension.")
-        cube = self.with_mask(goodchannels[:, None, None])
-        cube.goodbeams_mask = np.logical_and(goodchannels, self.goodbeams_mask)
+        cube = BaseSpectralCube.mask_channels(self, goodchannels)
+        cube.goodbeams_mask = np.logical_and(np.asarray(goodchannels, dtype='bool'), self.goodbeams_mask)
         return cube
 
     def spectral_interpolate(self, *args, **kwargs):

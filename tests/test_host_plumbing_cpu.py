@@ -54,3 +54,14 @@ def test_the_method_surface_reaches_the_library(host, use_dask):
         if use_dask:
             assert set(m.statistics()) == {'npts', 'min', 'max', 'sum', 'sumsq', 'mean', 'sigma', 'rms'}
     assert len(calls) > 15 and all(rc != 0 for rc, msg in calls)      # every call got as far as the missing device
+
+
+def test_mask_channels(host):
+    S, calls = host
+    cube = S.SpectralCube(np.zeros((4, 6, 8), dtype=np.float32), S.CubeWCS(**G.ADV_WCS), unit='K')
+    masked = cube.mask_channels([True, False, True, True])
+    assert isinstance(masked.mask, S.BooleanArrayMask) and masked.shape == cube.shape
+    with pytest.raises(ValueError, match="one-dimensional"):
+        cube.mask_channels(np.ones((4, 1), dtype=bool))
+    with pytest.raises(ValueError, match="length equal"):
+        cube.mask_channels([True, False])
