@@ -149,7 +149,10 @@ class FakeLib(object):
             s = np.where(cnt > 0, np.nansum(d, axis=0), np.nan)
             m2 = np.where(cnt > 0, np.nansum((d - s / np.maximum(cnt, 1)) ** 2, axis=0), np.nan)
             lo, hi = np.nanmin(f, axis=0), np.nanmax(f, axis=0)
-        for ptr, val, T in ((osum, s, np.float64), (ocnt, cnt, np.int32), (om2, m2, np.float64), (omin, lo, np.float32), (omax, hi, np.float32)):
+            ahi = np.argmax(np.where(np.isnan(f), -np.inf, f), axis=0); ahi[cnt == 0] = 0
+            alo = np.argmin(np.where(np.isnan(f), np.inf, f), axis=0); alo[cnt == 0] = 0
+        for ptr, val, T in ((osum, s, np.float64), (ocnt, cnt, np.int32), (om2, m2, np.float64), (omin, lo, np.float32), (omax, hi, np.float32),
+                            (oamin, alo, np.int32), (oamax, ahi, np.int32)):
             if ptr:
                 view(ptr, T, (ny, nx), (nx, 1))[...] = val
         return 0
