@@ -82,6 +82,7 @@ SIGNATURES = {
     'sc_wcs_pixel_map': (_i32, [_pd, _pd, _i64, _i64, _vp, _vp, _vp]),
     'sc_fits_decode': (_i32, [_vp, _vp, _i64, _i32, _dbl, _dbl, _i32, C.c_longlong, _vp]),
     'sc_reduce_axis0': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _pmask, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'sc_reduce_spatial': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _pmask, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'sc_synth_cube': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _vp, _i32, _i32, _vp]),
     'sc_last_kernel_ms': (C.c_float, [_i32]),
     'sc_enable_kernel_timing': (None, [_i32]),

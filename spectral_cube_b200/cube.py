@@ -826,16 +826,40 @@ class BaseSpectralCube(object):
                                        ptr('argmin'), ptr('argmax'), _stream()))
         return outs
 
+    def _reduce_spatial_raw(self, axis, want):
+        """`_reduce_axis0_raw` along numpy axis 1 or 2 (`sc_reduce_spatial`): name -> device tensor (nchan, nx | ny)."""
+        torch = _torch()
+        lib = _lib.load()
+        src = self._materialized()._data
+        nchan, ny, nx = self.shape
+        shape = (nchan, nx) if axis == 1 else (nchan, ny)
+        dt = {'sum': torch.float64, 'count': torch.int32, 'm2': torch.float64, 'min': torch.float32,
+              'max': torch.float32, 'argmin': torch.int32, 'argmax': torch.int32}
+        outs = dict((k, torch.empty(shape, dtype=dt[k], device=src.device)) for k in want)
+        ptr = lambda k: outs[k].data_ptr() if k in outs else None
+        desc, keep = self._mask_desc()
+        _lib.check(lib.sc_reduce_spatial(src.data_ptr(), nchan, ny, nx, src.stride(0), src.stride(1), int(axis), desc,
+                                         ptr('sum'), ptr('count'), ptr('m2'), ptr('min'), ptr('max'),
+                                         ptr('argmin'), ptr('argmax'), _stream()))
+        return outs
+
+    def _reduce_raw(self, axis, want):
+        return self._reduce_axis0_raw(want) if axis in (0, None) else self._reduce_spatial_raw(axis, want)
+
     def _reduction_axis(self, axis, name):
+        import os
+        if axis in (1, 2) and os.environ.get('SC_REDUCE_SPATIAL') == '1':
+            return                     # opt-in: `sc_reduce_spatial` has not run on hardware yet
         if axis not in (0, None):
             raise NotImplementedError("%s(axis=%r): only reductions along the spectral axis (axis=0) and over the "
                                       "whole cube (axis=None) run on the device; see SURVEY.md 8(f)" % (name, axis))
 
-    def _collapsed(self, values, unit):
-        """Projection of a collapsed spectral axis (spectral_cube.py:395-414)."""
-        meta = {'collapse_axis': 0}
+    def _collapsed(self, values, unit, axis=0):
+        """Projection of a collapsed axis (spectral_cube.py:395-414)."""
+        meta = {'collapse_axis': axis or 0}
         meta.update(self._meta)
-        return Projection(values, unit=unit, wcs=self._wcs.drop_axis(0), meta=meta, header=self._header, copy=False)
+        return Projection(values, unit=unit, wcs=self._wcs.drop_axis(axis or 0), meta=meta, header=self._header,
+                          copy=False)
 
     def _np_dtype(self):
         return np.float32          # the cube's dtype: the nan-functions of the reference keep it
@@ -845,48 +869,48 @@ class BaseSpectralCube(object):
     def sum(self, axis=None, how='auto', **kwargs):
         """Sum over the spectral axis (or everything); nothing included -> NaN (np_compat.allbadtonan)."""
         self._reduction_axis(axis, 'sum')
-        r = self._reduce_axis0_raw({'sum', 'count'} if axis is None else {'sum'})
+        r = self._reduce_raw(axis, {'sum', 'count'} if axis is None else {'sum'})
         if axis is None:
             return self._np_dtype()(whole_sum(_torch(), r['sum'], r['count']))
-        return self._collapsed(r['sum'].cpu().numpy().astype(self._np_dtype()), self._unit)
+        return self._collapsed(r['sum'].cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def mean(self, axis=None, how='cube', **kwargs):
         self._reduction_axis(axis, 'mean')
         torch = _torch()
-        r = self._reduce_axis0_raw({'sum', 'count'})
+        r = self._reduce_raw(axis, {'sum', 'count'})
         if axis is None:
             return self._np_dtype()(whole_mean(torch, r['sum'], r['count']))
         out = r['sum'] / r['count'].to(torch.float64)            # 0 / 0 never happens: sum is NaN there
-        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
+        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def std(self, axis=None, how='cube', ddof=0, **kwargs):
         self._reduction_axis(axis, 'std')
         torch = _torch()
         if axis is None:
-            r = self._reduce_axis0_raw({'sum', 'count', 'm2'})
+            r = self._reduce_raw(axis, {'sum', 'count', 'm2'})
             return self._np_dtype()(whole_std(torch, r['sum'], r['count'], r['m2'], ddof))
-        r = self._reduce_axis0_raw({'m2', 'count'})
+        r = self._reduce_raw(axis, {'m2', 'count'})
         n = r['count'].to(torch.float64) - float(ddof)
         out = torch.sqrt(r['m2'] / torch.where(n > 0, n, torch.full_like(n, float('nan'))))
-        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit)
+        return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def max(self, axis=None, how='auto', **kwargs):
         self._reduction_axis(axis, 'max')
-        m = self._reduce_axis0_raw({'max'})['max']
+        m = self._reduce_raw(axis, {'max'})['max']
         if axis is None:
             return self._np_dtype()(whole_extremum(_torch(), m, 'max'))
-        return self._collapsed(m.cpu().numpy(), self._unit)
+        return self._collapsed(m.cpu().numpy(), self._unit, axis)
 
     def min(self, axis=None, how='auto', **kwargs):
         self._reduction_axis(axis, 'min')
-        m = self._reduce_axis0_raw({'min'})['min']
+        m = self._reduce_raw(axis, {'min'})['min']
         if axis is None:
             return self._np_dtype()(whole_extremum(_torch(), m, 'min'))
-        return self._collapsed(m.cpu().numpy(), self._unit)
+        return self._collapsed(m.cpu().numpy(), self._unit, axis)
 
     def _arg_extremum(self, axis, which):
         self._reduction_axis(axis, 'arg' + which)
-        r = self._reduce_axis0_raw({which, 'arg' + which})
+        r = self._reduce_raw(axis, {which, 'arg' + which})
         if axis is not None:
             return r['arg' + which].cpu().numpy().astype(np.int64)
         return whole_arg_extremum(_torch(), r[which], r['arg' + which], which)

@@ -65,3 +65,24 @@ def test_mask_channels(host):
         cube.mask_channels(np.ones((4, 1), dtype=bool))
     with pytest.raises(ValueError, match="length equal"):
         cube.mask_channels([True, False])
+
+
+def test_spatial_axis_reductions_reach_the_library_when_opted_in(host, monkeypatch):
+    S, calls = host
+    from spectral_cube_b200.masks import LazyMask
+    cube = S.SpectralCube(np.zeros((4, 6, 8), dtype=np.float32), S.CubeWCS(**G.ADV_WCS), unit='K')
+    cube._mask = LazyMask(np.isfinite, cube=cube)
+    with pytest.raises(NotImplementedError):
+        cube.sum(axis=1)
+    monkeypatch.setenv('SC_REDUCE_SPATIAL', '1')
+    del calls[:]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for axis, shape in ((1, (4, 8)), (2, (4, 6))):
+            for name in ('sum', 'mean', 'std', 'max', 'min'):
+                out = getattr(cube, name)(axis=axis)
+                assert isinstance(out, S.Projection) and out.shape == shape and out.meta['collapse_axis'] == axis
+            assert cube.argmax(axis=axis).shape == shape and cube.argmin(axis=axis).dtype == np.int64
+    assert len(calls) == 14 and all(rc != 0 for rc, msg in calls)
+    with pytest.raises(NotImplementedError):
+        cube.sum(axis=3)

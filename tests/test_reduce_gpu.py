@@ -191,3 +191,37 @@ def test_reductions_on_views_with_odd_widths():
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         assert_maps_close(sub.mean(axis=0).value, osub.mean(axis=0), rtol=1e-5, atol=1e-6)
+
+
+# ---- along the spatial axes: sc_reduce_spatial (opt-in, SC_REDUCE_SPATIAL=1) ------------------------------------
+@pytest.mark.skipif(__import__('os').environ.get('SC_TEST_OPT_IN') != '1',
+                    reason="sc_reduce_spatial is opt-in and has not met hardware yet: set SC_TEST_OPT_IN=1 "
+                           "(tools/gpu_first_call.sh does)")
+@pytest.mark.parametrize('axis', [1, 2])
+@pytest.mark.parametrize('shape,maskname', [((5, 40, 64), 'isfinite'), ((3, 33, 70), 'gt3'), ((2, 7, 13), 'or'),
+                                            ((4, 1, 31), 'isfinite'), ((2, 300, 1), 'gt3')])
+def test_reductions_along_the_spatial_axes(shape, maskname, axis, monkeypatch):
+    monkeypatch.setenv('SC_REDUCE_SPATIAL', '1')
+    data, sc, oc = _pair(shape, maskname, 'spatial')
+    filled = oc._get_filled_data(fill=np.nan).astype(np.float64)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        cnt = (~np.isnan(filled)).sum(axis=axis)
+        want = {'sum': np.where(cnt > 0, np.nansum(filled, axis=axis), np.nan), 'mean': np.nanmean(filled, axis=axis),
+                'std': np.nanstd(filled, axis=axis), 'max': np.nanmax(filled, axis=axis), 'min': np.nanmin(filled, axis=axis)}
+        for name in ('sum', 'mean', 'std', 'max', 'min'):
+            got = getattr(sc, name)(axis=axis)
+            assert got.shape == want[name].shape and got.value.dtype == np.float32, name
+            assert_maps_close(got.value, want[name], rtol=RTOL, atol=1e-5, what='%s(axis=%d)' % (name, axis))
+            # the oracle method (numpy on the float32 cube, like the reference) agrees with the float64 statement
+            assert_maps_close(np.asarray(getattr(oc, name)(axis=axis), dtype=np.float64), want[name], rtol=1e-3, atol=1e-3,
+                              what='oracle %s' % name)
+        assert_maps_close(sc.std(axis=axis, ddof=1).value, np.nanstd(filled, axis=axis, ddof=1), rtol=RTOL, atol=1e-5,
+                          what='std ddof=1')
+    some = cnt > 0
+    inc = ~np.isnan(filled)
+    assert np.array_equal(sc.argmax(axis=axis)[some], np.argmax(np.where(inc, filled, -np.inf), axis=axis)[some])
+    assert np.array_equal(sc.argmin(axis=axis)[some], np.argmin(np.where(inc, filled, np.inf), axis=axis)[some])
+    assert (sc.argmax(axis=axis)[~some] == 0).all()
+    assert sc.sum(axis=axis).meta['collapse_axis'] == axis

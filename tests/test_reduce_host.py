@@ -104,3 +104,27 @@ def test_statistics_from_partials(seed):
     got = C.whole_statistics(torch, blank['sum'], blank['count'], blank['m2'], blank['min'], blank['max'])
     assert got['npts'] == 0 and got['sum'] == 0.0 and got['sumsq'] == 0.0
     assert all(np.isnan(got[k]) for k in ('min', 'max', 'mean', 'sigma', 'rms'))
+
+
+@pytest.mark.parametrize('nx', [1, 31, 32, 33, 100, 257])
+def test_model_of_the_spatial_reduction_merge_matches_numpy(nx):
+    """reduce_axis2_kernel (opt-in, csrc/reduce_spatial.cu) restated in Python: lanes striding over a row, shifted sums,
+    xor-butterfly merge with first-occurrence ties -- against numpy's nan-functions."""
+    from tools.dryrun.model_reduce_spatial import reduce_row
+    rng = np.random.default_rng(nx)
+    row = (3.0 + rng.normal(0, 2, nx)).astype(np.float32)
+    row[rng.random(nx) < 0.2] = np.nan
+    if nx > 40:
+        row[7] = row[39] = np.nanmax(row) + 1.0          # a tie between two lanes: the first position wins
+        row[5] = row[70] = np.nanmin(row) - 1.0
+    n, total, m2, lo, hi, ilo, ihi = reduce_row(row)
+    d = row.astype(np.float64)
+    assert n == int((~np.isnan(d)).sum())
+    if n == 0:
+        assert np.isnan(total) and np.isnan(m2) and (ilo, ihi) == (0, 0)
+        return
+    assert np.isclose(total, np.nansum(d), rtol=1e-13)
+    assert np.isclose(m2, np.nansum((d - np.nanmean(d)) ** 2), rtol=1e-10, atol=1e-12)
+    assert lo == np.nanmin(row) and hi == np.nanmax(row)
+    assert ilo == int(np.nanargmin(row)) and ihi == int(np.nanargmax(row))
+    assert reduce_row(np.full(nx, np.nan, dtype=np.float32))[0] == 0

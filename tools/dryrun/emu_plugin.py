@@ -137,7 +137,13 @@ class FakeLib(object):
         view(o0, np.float64, (ny, nx), (nx, 1))[...] = f.sum(axis=0) * pix_size
         return 0
 
+    def sc_reduce_spatial(self, cube, nchan, ny, nx, sc, sy, axis, mask, osum, ocnt, om2, omin, omax, oamin, oamax, stream):
+        return self._reduce(cube, nchan, ny, nx, sc, sy, axis, mask, osum, ocnt, om2, omin, omax, oamin, oamax)
+
     def sc_reduce_axis0(self, cube, nchan, ny, nx, sc, sy, mask, osum, ocnt, om2, omin, omax, oamin, oamax, stream):
+        return self._reduce(cube, nchan, ny, nx, sc, sy, 0, mask, osum, ocnt, om2, omin, omax, oamin, oamax)
+
+    def _reduce(self, cube, nchan, ny, nx, sc, sy, axis, mask, osum, ocnt, om2, omin, omax, oamin, oamax):
         import warnings
         shape = (nchan, ny, nx)
         data = view(cube, np.float32, shape, (sc, sy, 1))
@@ -145,16 +151,17 @@ class FakeLib(object):
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             d = f.astype(np.float64)
-            cnt = (~np.isnan(d)).sum(axis=0)
-            s = np.where(cnt > 0, np.nansum(d, axis=0), np.nan)
-            m2 = np.where(cnt > 0, np.nansum((d - s / np.maximum(cnt, 1)) ** 2, axis=0), np.nan)
-            lo, hi = np.nanmin(f, axis=0), np.nanmax(f, axis=0)
-            ahi = np.argmax(np.where(np.isnan(f), -np.inf, f), axis=0); ahi[cnt == 0] = 0
-            alo = np.argmin(np.where(np.isnan(f), np.inf, f), axis=0); alo[cnt == 0] = 0
+            cnt = (~np.isnan(d)).sum(axis=axis)
+            s = np.where(cnt > 0, np.nansum(d, axis=axis), np.nan)
+            m2 = np.where(cnt > 0, np.nansum((d - np.expand_dims(s / np.maximum(cnt, 1), axis)) ** 2, axis=axis), np.nan)
+            lo, hi = np.nanmin(f, axis=axis), np.nanmax(f, axis=axis)
+            ahi = np.argmax(np.where(np.isnan(f), -np.inf, f), axis=axis); ahi[cnt == 0] = 0
+            alo = np.argmin(np.where(np.isnan(f), np.inf, f), axis=axis); alo[cnt == 0] = 0
         for ptr, val, T in ((osum, s, np.float64), (ocnt, cnt, np.int32), (om2, m2, np.float64), (omin, lo, np.float32), (omax, hi, np.float32),
                             (oamin, alo, np.int32), (oamax, ahi, np.int32)):
             if ptr:
-                view(ptr, T, (ny, nx), (nx, 1))[...] = val
+                oshape = tuple(n for i, n in enumerate(shape) if i != axis)
+                view(ptr, T, oshape, (oshape[1], 1))[...] = val
         return 0
 
 

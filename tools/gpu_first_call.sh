@@ -8,6 +8,9 @@ mkdir -p gpurun_out
 # 1. the whole GPU suite WITHOUT -x: one run shows every failure of the files that never met hardware
 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/tests.log 2>&1
 tail -15 gpurun_out/tests.log
+# 1b. opt-in code that has not met hardware yet (sc_reduce_spatial)
+SC_TEST_OPT_IN=1 python -m pytest tests/test_reduce_gpu.py -m gpu -q -p no:cacheprovider -k spatial_axes > gpurun_out/tests_opt_in.log 2>&1
+tail -5 gpurun_out/tests_opt_in.log
 # 2. the bench line (configs[1]) and the reference arm
 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 600 gpurun_out/bench_n1.json
