@@ -162,6 +162,10 @@ if 'reduce' in which and world == 1:
     emit('reduce', 'sum+count+m2+min+max+argmin+argmax along the spectral axis in one pass, 2048x2048x1024', V, ms, 4 * V + 36 * ny * nx)
     ms = timeit(lambda: c._reduce_axis0_raw({'max'}))
     emit('reduce', 'max along the spectral axis (peak map)', V, ms, 4 * V + 4 * ny * nx)
+    if os.environ.get('SC_REDUCE_SPATIAL') == '1':                     # opt-in kernels (sc_reduce_spatial)
+        for axis in (1, 2):
+            ms = timeit(lambda: c._reduce_spatial_raw(axis, allstats))
+            emit('reduce', 'all seven statistics along numpy axis %d (sc_reduce_spatial)' % axis, V, ms, 4 * V)
     del dev, c
     torch.cuda.empty_cache()
 

@@ -17,6 +17,8 @@ tail -c 600 gpurun_out/bench_n1.json
 # 3. convolve_to: round / elliptical / per-channel beams and the sc_scale epilogue on its own
 python tools/bench_configs.py convolve > gpurun_out/configs_convolve.jsonl 2> gpurun_out/configs_convolve.err
 cat gpurun_out/configs_convolve.jsonl
+SC_REDUCE_SPATIAL=1 python tools/bench_configs.py reduce > gpurun_out/configs_reduce.jsonl 2> gpurun_out/configs_reduce.err
+cat gpurun_out/configs_reduce.jsonl
 # 4. launch list of the same bench command (shares of the step), then one full capture of the convolve_to kernels
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 > gpurun_out/b.log 2>&1
