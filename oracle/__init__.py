@@ -23,6 +23,11 @@ spectral_cube`` fails at ``spectral_cube/spectral_cube.py:14`` (dask) / ``:16``
   * ``numpy.interp`` / ``scipy.interpolate.interp1d`` (both importable here; call
     sites ``spectral_cube.py:3302-3310``, ``dask_spectral_cube.py:1346-1349``)
                                                     -> ``oracle/interp.py`` (calls the real functions)
+  * ``astropy.convolution.convolve_fft`` (the numpy class's default in ``convolve_to``,
+    ``spectral_cube.py:3336, 4128``)                 -> ``oracle/convolve.py:convolve_fft``
+  * ``radio_beam.Beam.deconvolve / as_kernel / sr`` (radio-beam>=0.3.5, ``pyproject.toml:32``,
+    not installed; call sites ``spectral_cube.py:3361-3378, 4186-4209``)
+                                                    -> ``oracle/beam.py``
   * ``reproject.reproject_interp`` (reproject>=0.9.1, not installed)
                                                     -> ``oracle/reproject.py``
   * ``astropy.wcs`` (wcslib; linear spectral + TAN/SIN/CAR celestial)
@@ -34,7 +39,9 @@ against every value-carrying golden the reference's own tests hold for the path:
 the ``> 4 K`` mask consistency test), ``tests/test_spectral_cube.py:2372-2383,
 2410-2421`` (Gaussian2DKernel / Tophat2DKernel spatial smoothing, 7 decimals),
 ``tests/test_regrid.py:138-172`` (spectral smoothing of a delta), ``:234-248,
-292-303, 318-345, 350-361`` (spectral interpolation).  ``reproject`` has no value
+292-303, 318-345, 350-361`` (spectral interpolation); ``tests/test_convolve_to_host.py`` does the same for
+``convolve_to``: ``tests/test_regrid.py:33-101``, ``tests/test_spectral_cube.py:2150-2225`` with the fixtures of
+``conftest.py:590-660``.  ``reproject`` has no value
 golden in the reference (``tests/test_regrid.py:99-135`` checks shape/WCS only) and
 the package is absent: **bilinear reproject parity is unpinned** (restated from
 the published algorithm; see ``oracle/reproject.py``).
