@@ -1374,6 +1374,7 @@ class DaskVaryingResolutionSpectralCube(VaryingResolutionSpectralCube):
 
 
 VaryingResolutionSpectralCube._result_class = SpectralCube
+DaskVaryingResolutionSpectralCube.statistics = DaskSpectralCube.statistics        # DaskSpectralCubeMixin (dask:769-814)
 DaskVaryingResolutionSpectralCube._result_class = DaskSpectralCube
 
 
