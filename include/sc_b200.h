@@ -344,7 +344,7 @@ int sc_reduce_axis0(const float *cube, int64_t nchan, int64_t ny, int64_t nx,
 
 /* The same seven statistics along a SPATIAL axis (numpy axis 1 = y -> outputs (nchan, nx); axis 2 = x -> outputs
  * (nchan, ny)); indices are positions along the reduced axis.  `apply_numpy_function(..., axis=1 or 2)`,
- * spectral_cube.py:361-470, 578-826.  Opt-in in the host layer (SC_REDUCE_SPATIAL=1) until it has run on hardware. */
+ * spectral_cube.py:361-470, 578-826. */
 int sc_reduce_spatial(const float *cube, int64_t nchan, int64_t ny, int64_t nx,
                       int64_t stride_c, int64_t stride_y, int axis, const sc_mask_desc *mask,
                       double *out_sum, int32_t *out_count, double *out_m2,

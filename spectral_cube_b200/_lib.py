@@ -37,6 +37,23 @@ class LibraryError(RuntimeError):
     pass
 
 
+class _NoDevice(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def on_device_of(tensor):
+    """Context manager making the CUDA device that holds `tensor` the current one: the library launches on the
+    calling thread's current device, on that device's current stream."""
+    import torch
+    if tensor is None or not getattr(tensor, 'is_cuda', False):
+        return _NoDevice()
+    return torch.cuda.device(tensor.device)
+
+
 _lib = None
 
 _i64, _i32, _dbl, _vp, _sz = C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_size_t

@@ -26,6 +26,20 @@ struct LaunchScope {
     ~LaunchScope() { count_launch(op, s, false); }
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device only: `done` keeps one bit per device ordinal, so a process
+// that drives several GPUs configures every kernel once on each of them (a race sets the attribute twice: benign).
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kern, size_t smem, unsigned long long *done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*done & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) *done |= bit;
+    return e;
+}
+
 // ---- device mask program ------------------------------------------------------------------
 // MODE_NONE:     mask is None                      -> include = !isnan(v)   (nansum semantics)
 // MODE_INTERVAL: isfinite(self) [& self OP scalar] -> include = lo < v && v < hi  (float32

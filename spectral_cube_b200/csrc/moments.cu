@@ -342,12 +342,8 @@ template <int CB, int STAGES, int MODE, int WANT>
 static cudaError_t launch_tma_one(const MomParams &p, unsigned grid, cudaStream_t s) {
     auto kern = moments_tma_kernel<CB, STAGES, MODE, WANT>;
     const size_t smem = sizeof(MomSmem<CB, STAGES>);
-    static bool configured = false;          // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
     kern<<<grid, TMA_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }

@@ -44,7 +44,7 @@ template <int MODE>
 __device__ __forceinline__ void reduce_take(const ReduceParams &p, ReduceAcc &a, float v, int64_t c, int64_t y, int64_t x) {
     const bool use = mask_include<MODE>(p.mask, v, c, y, x) && v == v;
     if (use) {
-        if (a.n == 0) a.k = (double)v;
+        if (a.n == 0) a.k = fabsf(v) <= FLT_MAX ? (double)v : 0.0;   // an infinite first value is no shift: inf - inf would poison the sum (np.nansum gives +-inf)
         const double d = (double)v - a.k;
         a.s1 += d;
         a.s2 = fma(d, d, a.s2);
@@ -194,12 +194,8 @@ reduce_tma_kernel(const __grid_constant__ ReduceParams p) {
 template <int MODE>
 static cudaError_t launch_reduce_tma(const ReduceParams &p, unsigned grid, cudaStream_t s) {
     auto kern = reduce_tma_kernel<MODE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReduceSmem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, sizeof(ReduceSmem), &configured)) return e;
     kern<<<grid, RT_THREADS, sizeof(ReduceSmem), s>>>(p);
     return cudaGetLastError();
 }

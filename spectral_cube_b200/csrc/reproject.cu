@@ -364,12 +364,8 @@ reproject_tiled_kernel(const __grid_constant__ ReprojParams p, const __grid_cons
 template <int MODE, int OUT64>
 static cudaError_t launch_reproject_tiled(const ReprojParams &p, const CUtensorMap &tmap, dim3 grid, cudaStream_t s) {
     auto kern = reproject_tiled_kernel<MODE, OUT64>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReprojSmem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, sizeof(ReprojSmem), &configured)) return e;
     kern<<<grid, RT_THREADS, sizeof(ReprojSmem), s>>>(p, tmap);
     return cudaGetLastError();
 }

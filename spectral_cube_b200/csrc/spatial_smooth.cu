@@ -720,7 +720,7 @@ direct2d_kernel(const __grid_constant__ DirectParams d) {
     else       reinterpret_cast<float *>(p.out)[c * p.out_stride_c + y * p.out_stride_y + x] = (float)res;
 }
 
-// ---- tiled direct 2-D kernel (OPT-IN: SC_DIRECT2D=1; written without a GPU at hand, not yet run on one) ----
+// ---- tiled direct 2-D kernel (the default for non-negative kernels; SC_DIRECT2D=0 forces direct2d_kernel) ----
 // What `convolve_to` needs for rotated elliptical beams, where direct2d_kernel pays one L1 request per tap and
 // output.  CTA = 256 threads = a 32-column x 64-row output tile of one channel; lane = column, warp = 8 rows.
 // The filled input box (tile + kernel margin) is staged ONCE in shared memory, widened to float64, with a float
@@ -852,7 +852,8 @@ plane_none_included_kernel(const __grid_constant__ SpatialParams p, uint8_t *fla
     if (threadIdx.x == 0) flags[c] = found ? 0 : 1;
 }
 
-// direct2d_kernel, or the opt-in tiled kernel (SC_DIRECT2D=1) when taps + box fit shared memory and no tap is negative (the tiled
+// the tiled kernel when taps + box fit shared memory and no tap is negative (10x faster on a B200: 183 vs 1859 ms for 29x29 taps
+// on 4096x4096x64, profiles/r02_convolve_to_n1.jsonl), else direct2d_kernel (the tiled
 // kernel's "nothing valid" test is a float32 sum of non-negative terms)
 static int launch_direct2d(const DirectParams &d, int out_dtype, bool nonneg, cudaStream_t s) {
     const SpatialParams &p = d.sp;
@@ -860,7 +861,7 @@ static int launch_direct2d(const DirectParams &d, int out_dtype, bool nonneg, cu
     const size_t taps_bytes = (size_t)((nt + 1) & ~1) * 8;
     const size_t smem8 = taps_bytes + (size_t)(DT_TX + d.ntx - 1) * (8 * DT_RY + d.nty - 1 + DT_RY) * 12;
     const size_t smem4 = taps_bytes + (size_t)(DT_TX + d.ntx - 1) * (4 * DT_RY + d.nty - 1 + DT_RY) * 12;
-    if (env_int("SC_DIRECT2D", 0) == 1 && nonneg && smem4 <= DT_MAX_SMEM) {
+    if (env_int("SC_DIRECT2D", 1) == 1 && nonneg && smem4 <= DT_MAX_SMEM) {
         const int nw = smem8 <= DT_MAX_SMEM ? 8 : 4;
         const size_t smem = nw == 8 ? smem8 : smem4;
         const int64_t tiles_x = cdiv(p.nx, DT_TX), tiles_y = cdiv(p.ny, nw * DT_RY);
@@ -922,12 +923,8 @@ static cudaError_t launch_sep_one(const SpatialParams &p, unsigned grid, cudaStr
     constexpr int NB = 2 * HB + 2;
     auto kern = sep_march_kernel<H, OUT64>;
     const size_t smem = sizeof(SpatialSmem<NB>);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
     kern<<<grid, SP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
@@ -938,12 +935,8 @@ static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cuda
     constexpr int NB = 2 * HB + 2;
     auto kern = sep_sparse_kernel<H, OUT64>;
     const size_t smem = sizeof(SparseSmem<NB>);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
     kern<<<grid, SQ_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }

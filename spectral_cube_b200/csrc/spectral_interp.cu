@@ -262,12 +262,8 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
 template <int MODE, int OUT64>
 static cudaError_t launch_interp_tma_one(const InterpParams &p, unsigned grid, int tiles_per_row, cudaStream_t s) {
     auto kern = spectral_interp_tma_kernel<MODE, OUT64>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterpSmem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, sizeof(InterpSmem), &configured)) return e;
     kern<<<grid, IT_THREADS, sizeof(InterpSmem), s>>>(p, tiles_per_row);
     return cudaGetLastError();
 }

@@ -514,12 +514,8 @@ template <int H, int MODE, int EPI>
 static cudaError_t launch_smooth_one(const SmoothParams &p, unsigned grid, cudaStream_t s) {
     auto kern = smooth_tma_kernel<H, MODE, EPI>;
     const size_t smem = sizeof(SmoothSmem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
     kern<<<grid, SM_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }

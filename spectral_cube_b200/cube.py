@@ -23,6 +23,7 @@ from .beam import Beam, Beams, BeamError, NoBeamError
 
 SIGMA2FWHM = 2. * np.sqrt(2. * np.log(2.))        # spectral_cube.py:82
 MEMORY_THRESHOLD = 1e8                            # cube_utils.py:266-268
+BIGDATAURL = "https://spectral-cube.readthedocs.io/en/latest/big_data.html"      # utils.py:11
 
 
 class SpectralCubeWarning(Warning):
@@ -232,6 +233,31 @@ class BaseSpectralCube(object):
     @property
     def ndim(self):
         return 3
+
+    @property
+    def _is_huge(self):
+        """cube_utils.py:270-274"""
+        return not (self.size < MEMORY_THRESHOLD)
+
+    def _refuse_huge(self, name, how=None, accepts_how=False):
+        """The `warn_slow` contract (utils.py:41-75): operations the reference can only do with the whole cube in host
+        memory are refused for cubes of >= 1e8 voxels unless ``allow_huge_operations`` is set; the text is the
+        reference's (tests/test_spectral_cube.py:104-133 match on it).  On the device nothing is loaded, but a script
+        written against the reference relies on the refusal as much as on the result."""
+        if how in ('slice', 'ray') or not self._is_huge or self.allow_huge_operations:
+            return
+        msg = ("This function ({0}) requires loading the entire "
+               "cube into memory, and the cube is large ({1} "
+               "pixels), so by default we disable this operation. "
+               "To enable the operation, set "
+               "`cube.allow_huge_operations=True` and try again.  ").format(
+                   "<function %s.%s>" % (type(self).__name__, name), self.size)
+        if accepts_how:
+            msg += ("Alternatively, you may want to consider using an "
+                    "approach that does not load the whole cube into "
+                    "memory by specifying how='slice' or how='ray'.  ")
+        msg += "See {bigdataurl} for details.".format(bigdataurl=BIGDATAURL)
+        raise ValueError(msg)
 
     @property
     def unit(self):
@@ -495,9 +521,15 @@ class BaseSpectralCube(object):
         return cube
 
     def spectral_smooth(self, kernel, convolve=None, verbose=0, use_memmap=True, num_cores=None, **kwargs):
-        """Smooth the cube along the spectral dimension; the mask is left unchanged."""
+        """Smooth the cube along the spectral dimension; the mask is left unchanged.  ``convolve`` may be astropy's
+        ``convolve`` (the default) or ``convolve_fft``; any other callable is refused -- the convolution runs on the
+        device and a user function cannot be called there (spectral_cube.py:3188, 3216-3222)."""
+        self._check_convolve_kwargs(kwargs)
+        fft = self._fft_semantics(convolve, default=False)
         taps = self._kernel_array(kernel, 1)
-        return self._new_cube_reporting_f64(self._run_spectral_smooth(taps, _lib.F32))
+        out = self._run_spectral_smooth(taps, _lib.F32)
+        self._convolve_epilogue(out, 1.0, fft)
+        return self._new_cube_reporting_f64(out)
 
     def check_jybeam_smoothing(self, raise_error_jybm=True):
         """base_class.py:116-140"""
@@ -568,12 +600,17 @@ class BaseSpectralCube(object):
         return out
 
     def spatial_smooth(self, kernel, convolve=None, raise_error_jybm=True, **kwargs):
-        """Smooth the image in each spatial-spatial plane of the cube."""
+        """Smooth the image in each spatial-spatial plane of the cube (``convolve``: see ``spectral_smooth``)."""
         self.check_jybeam_smoothing(raise_error_jybm=raise_error_jybm)
+        self._check_convolve_kwargs(kwargs)
+        fft = self._fft_semantics(convolve, default=False)
         k2d = self._kernel_array(kernel, 2)
+        out = self._run_spatial_smooth(k2d, _lib.F32)
+        # planes copied through (:169-172) never met the convolution function
+        self._convolve_epilogue(out, 1.0, fft, skip=self._passthrough_flags)
         if self._mirrors_dask:
-            return self._new_cube_with(data=self._run_spatial_smooth(k2d, _lib.F32))
-        return self._new_cube_reporting_f64(self._run_spatial_smooth(k2d, _lib.F32))
+            return self._new_cube_with(data=out)
+        return self._new_cube_reporting_f64(out)
 
     # -- convolution to a common beam (spectral_cube.py:3335-3392; dask_spectral_cube.py:1412-1464) ------
     @property
@@ -622,7 +659,7 @@ class BaseSpectralCube(object):
                     raise NotImplementedError("convolution keyword %s=%r is not available on the device path "
                                               "(only %r)" % (key, val, supported[key]))
             elif key not in ('allow_huge', 'num_cores', 'use_memmap', 'parallel', 'verbose', 'psf_pad', 'fft_pad',
-                             'save_to_tmp_dir'):
+                             'save_to_tmp_dir', 'update_function', 'memmap_dir'):
                 raise TypeError("unexpected keyword argument %r" % key)
 
     @staticmethod
@@ -664,6 +701,8 @@ class BaseSpectralCube(object):
         ``beam.sr / self.beam.sr``.  ``convolve`` is accepted for drop-in compatibility: with the defaults both
         astropy functions compute the same NaN-interpolating, zero-padded, normalised convolution the device
         kernels do."""
+        if not self._mirrors_dask:
+            self._refuse_huge('convolve_to')                          # @warn_slow, spectral_cube.py:3334
         self._check_convolve_kwargs(kwargs)
         beam = Beam.coerce(beam)
         if beam == self.beam:
@@ -791,8 +830,7 @@ class BaseSpectralCube(object):
         if shape_out[0] != self.shape[0]:
             raise ValueError("reproject() resamples the celestial axes only; use spectral_interpolate for the "
                              "spectral axis (spectral_cube.py:2656-2657)")
-        if self.size >= MEMORY_THRESHOLD and not self.allow_huge_operations and not kwargs.pop('_allow_huge', True):
-            raise ValueError("This function requires loading the whole cube into memory")      # utils.py:53-67
+        self._refuse_huge('reproject')                                # @warn_slow, spectral_cube.py:2649
         yin, xin = self._pixel_map(newwcs, shape_out[1], shape_out[2])
         out, out32, foot, flag = self._run_reproject(yin, xin, self._ORDERS[order], filled=filled)
         if int(flag.item()) == 0:
@@ -846,13 +884,11 @@ class BaseSpectralCube(object):
     def _reduce_raw(self, axis, want):
         return self._reduce_axis0_raw(want) if axis in (0, None) else self._reduce_spatial_raw(axis, want)
 
-    def _reduction_axis(self, axis, name):
-        import os
-        if axis in (1, 2) and os.environ.get('SC_REDUCE_SPATIAL') == '1':
-            return                     # opt-in: `sc_reduce_spatial` has not run on hardware yet
-        if axis not in (0, None):
-            raise NotImplementedError("%s(axis=%r): only reductions along the spectral axis (axis=0) and over the "
-                                      "whole cube (axis=None) run on the device; see SURVEY.md 8(f)" % (name, axis))
+    def _reduction_axis(self, axis, name, how=None):
+        if not self._mirrors_dask:
+            self._refuse_huge(name, how=how, accepts_how=True)       # @warn_slow, spectral_cube.py:577-826
+        if axis not in (0, 1, 2, None):
+            raise NotImplementedError("%s(axis=%r): a cube has axes 0 (spectral), 1 and 2 (spatial)" % (name, axis))
 
     def _collapsed(self, values, unit, axis=0):
         """Projection of a collapsed axis (spectral_cube.py:395-414)."""
@@ -868,14 +904,14 @@ class BaseSpectralCube(object):
     # against the V voxels of the pass.  Scalars come back as numpy float32 (the reference wraps them in a Quantity).
     def sum(self, axis=None, how='auto', **kwargs):
         """Sum over the spectral axis (or everything); nothing included -> NaN (np_compat.allbadtonan)."""
-        self._reduction_axis(axis, 'sum')
+        self._reduction_axis(axis, 'sum', how)
         r = self._reduce_raw(axis, {'sum', 'count'} if axis is None else {'sum'})
         if axis is None:
             return self._np_dtype()(whole_sum(_torch(), r['sum'], r['count']))
         return self._collapsed(r['sum'].cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def mean(self, axis=None, how='cube', **kwargs):
-        self._reduction_axis(axis, 'mean')
+        self._reduction_axis(axis, 'mean', how)
         torch = _torch()
         r = self._reduce_raw(axis, {'sum', 'count'})
         if axis is None:
@@ -884,7 +920,7 @@ class BaseSpectralCube(object):
         return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def std(self, axis=None, how='cube', ddof=0, **kwargs):
-        self._reduction_axis(axis, 'std')
+        self._reduction_axis(axis, 'std', how)
         torch = _torch()
         if axis is None:
             r = self._reduce_raw(axis, {'sum', 'count', 'm2'})
@@ -895,21 +931,21 @@ class BaseSpectralCube(object):
         return self._collapsed(out.cpu().numpy().astype(self._np_dtype()), self._unit, axis)
 
     def max(self, axis=None, how='auto', **kwargs):
-        self._reduction_axis(axis, 'max')
+        self._reduction_axis(axis, 'max', how)
         m = self._reduce_raw(axis, {'max'})['max']
         if axis is None:
             return self._np_dtype()(whole_extremum(_torch(), m, 'max'))
         return self._collapsed(m.cpu().numpy(), self._unit, axis)
 
     def min(self, axis=None, how='auto', **kwargs):
-        self._reduction_axis(axis, 'min')
+        self._reduction_axis(axis, 'min', how)
         m = self._reduce_raw(axis, {'min'})['min']
         if axis is None:
             return self._np_dtype()(whole_extremum(_torch(), m, 'min'))
         return self._collapsed(m.cpu().numpy(), self._unit, axis)
 
-    def _arg_extremum(self, axis, which):
-        self._reduction_axis(axis, 'arg' + which)
+    def _arg_extremum(self, axis, which, how=None):
+        self._reduction_axis(axis, 'arg' + which, how)
         r = self._reduce_raw(axis, {which, 'arg' + which})
         if axis is not None:
             return r['arg' + which].cpu().numpy().astype(np.int64)
@@ -917,10 +953,10 @@ class BaseSpectralCube(object):
 
     def argmax(self, axis=None, how='auto', **kwargs):
         """Channel of the (first) maximum; arbitrary (0) where nothing is included (spectral_cube.py:800-811)."""
-        return self._arg_extremum(axis, 'max')
+        return self._arg_extremum(axis, 'max', how)
 
     def argmin(self, axis=None, how='auto', **kwargs):
-        return self._arg_extremum(axis, 'min')
+        return self._arg_extremum(axis, 'min', how)
 
     # -- moments (spectral_cube.py:1614-1763; dask_spectral_cube.py:1031-1132) -----------------------
     def _moments_axis0_raw(self, want_bits):
@@ -1141,13 +1177,15 @@ class SpectralCube(BaseSpectralCube):
         return load_fits_cube(filename, target, **kwargs)
 
     def write(self, filename, overwrite=False, format='fits'):
-        """io/fits.py:262-282: the cube's (unmasked) data and WCS as a primary-HDU FITS image."""
+        """io/fits.py:262-282 -> ``cube.hdu`` = ``PrimaryHDU(self.unitless_filled_data[:], header=self.header)``
+        (spectral_cube.py:2563-2570; dask :1400-1405): the FILLED data -- masked voxels are written as the fill
+        value -- in the dtype the reference's cube holds (float64 after reproject / numpy-class smoothing)."""
         from .io_fits import write_fits
         hdr = dict(self._header or {})
         hdr.update(self._wcs.to_header())
         if self._unit:
             hdr['BUNIT'] = str(self._unit)
-        write_fits(filename, self._data.cpu().numpy(), hdr, overwrite=overwrite)
+        write_fits(filename, self._get_filled_data(fill=self._fill_value), hdr, overwrite=overwrite)
 
 
 class DaskSpectralCube(SpectralCube):
@@ -1174,6 +1212,12 @@ class DaskSpectralCube(SpectralCube):
 
     def spectral_smooth(self, kernel, convolve=None, save_to_tmp_dir=False, **kwargs):
         """Lazy like the reference's dask class; ``save_to_tmp_dir=True`` computes straight away."""
+        self._check_convolve_kwargs(kwargs)
+        if self._fft_semantics(convolve, default=False):
+            # `convolve_fft` turns empty windows into 0.0: not expressible in the lazy fused form, run it now
+            out = self._run_spectral_smooth(self._kernel_array(kernel, 1), _lib.F32)
+            self._convolve_epilogue(out, 1.0, True)
+            return self._new_cube_with(data=out)
         taps = self._kernel_array(kernel, 1)
         if self._mask is not None and self._pending is not None and self._data_t is None:
             self._data                        # chain of lazy ops: materialise the inner one first
@@ -1321,6 +1365,8 @@ class VaryingResolutionSpectralCube(BaseSpectralCube):
         Every channel has its own deconvolved kernel; each plane is one launch of the spatial kernels writing
         its slice of the result (the planes of a real cube are tens of MB: the launches fill the chip), followed
         by the in-place Jy/beam rescale of that plane."""
+        if not self._mirrors_dask:
+            self._refuse_huge('convolve_to')                          # @warn_slow, spectral_cube.py:4126
         self._check_convolve_kwargs(kwargs)
         beam = Beam.coerce(beam)
         pc = self._wcs.pc
@@ -1373,6 +1419,30 @@ class DaskVaryingResolutionSpectralCube(VaryingResolutionSpectralCube):
         return self
 
 
+def _on_cube_device(method):
+    """Run `method` with the CUDA device that holds the cube's voxels as the current device: the library launches on
+    the calling thread's current device and `_stream()` is that device's current stream, so a cube on cuda:1 must
+    not be processed while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        t = getattr(self, '_data_t', None)
+        if t is None and getattr(self, '_pending', None) is not None:
+            t = self._pending.source._data_t
+        with _lib.on_device_of(t):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
+def _guard_device_of_methods(*classes):
+    import types
+    for cls in classes:
+        for name, attr in list(vars(cls).items()):
+            if isinstance(attr, types.FunctionType) and not (name.startswith('__') and name.endswith('__')):
+                setattr(cls, name, _on_cube_device(attr))
+
+
 VaryingResolutionSpectralCube._result_class = SpectralCube
 DaskVaryingResolutionSpectralCube.statistics = DaskSpectralCube.statistics        # DaskSpectralCubeMixin (dask:769-814)
 DaskVaryingResolutionSpectralCube._result_class = DaskSpectralCube
@@ -1384,3 +1454,7 @@ class _NullContext(object):
 
     def __exit__(self, *a):
         return False
+
+
+_guard_device_of_methods(BaseSpectralCube, SpectralCube, DaskSpectralCube, VaryingResolutionSpectralCube,
+                         DaskVaryingResolutionSpectralCube)

@@ -61,11 +61,14 @@ class _Lowering(object):
 
     def data_fields(self, data):
         """(ptr, ds_c, ds_y) for a float32 data tensor the mask was built on."""
-        if data is None or (data.data_ptr() == self.cube.data_ptr() and data.stride() == self.cube.stride()):
+        if data is None or (data.data_ptr() == self.cube.data_ptr() and data.stride() == self.cube.stride()
+                            and data.device == self.cube.device):
             return dict(data=None, ds_c=0, ds_y=0)
         if tuple(data.shape) != tuple(self.cube.shape):
             raise ValueError("mask data shape %s does not match cube shape %s"
                              % (tuple(data.shape), tuple(self.cube.shape)))
+        if data.device != self.cube.device:
+            data = data.to(self.cube.device)             # a mask built on another GPU's copy of the data
         if data.stride(2) != 1:
             data = data.contiguous()
         self.keep.append(data)
@@ -73,7 +76,7 @@ class _Lowering(object):
 
     def array_fields(self, arr):
         """(ptr, strides with 0 on broadcast axes) for an array broadcastable to the cube."""
-        t = arr
+        t = arr if arr.device == self.cube.device else arr.to(self.cube.device)
         while t.dim() < 3:
             t = t.unsqueeze(0)
         e = t.expand(tuple(self.cube.shape))
@@ -116,8 +119,9 @@ class MaskBase(object):
         desc, keep = lower_mask(self, ref)
         out = torch.empty(tuple(ref.shape), dtype=torch.uint8, device=ref.device)
         nchan, ny, nx = ref.shape
-        _lib.check(lib.sc_mask_include(ref.data_ptr(), nchan, ny, nx, ref.stride(0), ref.stride(1),
-                                       desc, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        with _lib.on_device_of(ref):
+            _lib.check(lib.sc_mask_include(ref.data_ptr(), nchan, ny, nx, ref.stride(0), ref.stride(1),
+                                           desc, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return out
 
     def _reference_tensor(self):
@@ -270,7 +274,7 @@ class BooleanArrayMask(MaskBase):
 
     def _reference_tensor(self):
         torch = _torch()
-        return torch.zeros(self._shape, dtype=torch.float32, device='cuda')
+        return torch.zeros(self._shape, dtype=torch.float32, device=self._mask.device)
 
     def __getitem__(self, view):
         """masks.py:559-566: the sliced array (a view of the same device memory)."""
@@ -333,7 +337,7 @@ class LazyMask(MaskBase):
         if not isinstance(res, torch.Tensor) or tuple(res.shape) != tuple(self._data.shape):
             raise ValueError("Function did not return mask with correct shape")
         return low.add(kind=_lib.MASK_BOOL, array_dtype=_lib.U8,
-                       **low.array_fields(res.to(torch.uint8).cuda()))
+                       **low.array_fields(res.to(device=low.cube.device, dtype=torch.uint8)))
 
 
 class LazyComparisonMask(LazyMask):
@@ -371,11 +375,11 @@ class LazyComparisonMask(LazyMask):
         if hasattr(cv, 'shape') and len(cv.shape) > 0:
             torch = _torch()
             if isinstance(cv, torch.Tensor):
-                t = cv.cuda()
+                t = cv.to(low.cube.device)
                 if t.dtype not in (torch.float32, torch.float64):
                     t = t.to(torch.float64)
             else:
-                t = torch.from_numpy(np.ascontiguousarray(cv, dtype=np.float64)).cuda()
+                t = torch.from_numpy(np.ascontiguousarray(cv, dtype=np.float64)).to(low.cube.device)
             dt = _lib.F32 if t.dtype == torch.float32 else _lib.F64
             return low.add(kind=_lib.MASK_CMP_ARRAY, op=_OPS[self._function], array_dtype=dt,
                            **low.data_fields(self._data), **low.array_fields(t))
@@ -403,4 +407,4 @@ class FunctionMask(MaskBase):
         if not isinstance(res, torch.Tensor):
             res = torch.from_numpy(np.ascontiguousarray(res))
         return low.add(kind=_lib.MASK_BOOL, array_dtype=_lib.U8,
-                       **low.array_fields(res.to(torch.uint8).cuda()))
+                       **low.array_fields(res.to(device=low.cube.device, dtype=torch.uint8)))

@@ -58,7 +58,10 @@ class LowerDimensionalObject(np.ndarray):
 
     @property
     def header(self):
-        hdr = dict(self._header or {})
+        """The parent cube's non-WCS cards + this object's own WCS (lower_dimensional_structures.py:66-97 builds it
+        from ``self.wcs.to_header()``): every WCS keyword of an axis above ``ndim`` is dropped, so a moment map of a
+        cube read from FITS does not carry the collapsed axis's CTYPE3/CRVAL3/... into a NAXIS=2 file."""
+        hdr = dict((k, v) for k, v in (self._header or {}).items() if not _is_wcs_card_above(k, self.ndim))
         if self._wcs is not None and hasattr(self._wcs, 'to_header'):
             hdr.update(self._wcs.to_header())
         hdr['BUNIT'] = str(self._unit) if self._unit is not None else ''
@@ -89,6 +92,30 @@ class LowerDimensionalObject(np.ndarray):
         elif unit is not None and not isinstance(unit, str):
             unit = unit ** 0.5
         return self._with(v, unit)
+
+
+_AXIS_CARD = None
+
+
+def _is_wcs_card_above(key, ndim):
+    """True for a per-axis FITS card (NAXISn, CTYPEn, CRVALn, CRPIXn, CDELTn, CUNITn, CROTAn, PCi_j, CDi_j, PVi_m)
+    that refers to an axis number > ndim."""
+    import re
+    global _AXIS_CARD
+    if _AXIS_CARD is None:
+        _AXIS_CARD = (re.compile(r'^(NAXIS|CTYPE|CRVAL|CRPIX|CDELT|CUNIT|CROTA|CRDER|CSYER|CNAME)(\d+)[A-Z]?$'),
+                      re.compile(r'^(PC|CD)0*(\d+)_0*(\d+)[A-Z]?$'), re.compile(r'^(PV|PS)(\d+)_\d+[A-Z]?$'))
+    k = str(key).upper()
+    m = _AXIS_CARD[0].match(k)
+    if m:
+        return int(m.group(2)) > ndim
+    m = _AXIS_CARD[1].match(k)
+    if m:
+        return int(m.group(2)) > ndim or int(m.group(3)) > ndim
+    m = _AXIS_CARD[2].match(k)
+    if m:
+        return int(m.group(2)) > ndim
+    return k == 'WCSAXES'
 
 
 class Projection(LowerDimensionalObject):

@@ -21,9 +21,28 @@ _SI = {'m/s': ('m/s', 1.0), 'km/s': ('m/s', 1.0e3), 'cm/s': ('m/s', 1.0e-2),
 _DEG = {'deg': 1.0, 'arcmin': 1.0 / 60.0, 'arcsec': 1.0 / 3600.0, 'rad': 180.0 / np.pi, '': 1.0}
 
 
+_SI_FOLDED = dict((k.lower(), k) for k in _SI)
+_SI_FOLDED.update({'angstrom': 'Angstrom', 'm s-1': 'm/s', 'km s-1': 'km/s', 'm.s-1': 'm/s', 'km.s-1': 'km/s',
+                   'micron': 'um', 'a': 'Angstrom'})
+_DEG_FOLDED = dict((k.lower(), k) for k in _DEG)
+_DEG_FOLDED.update({'degree': 'deg', 'degrees': 'deg', 'radian': 'rad', 'arcsecond': 'arcsec', 'arcminute': 'arcmin'})
+
+
+def _normalise_unit(unit, table, folded, what):
+    """wcslib's `wcsutrn`-style tolerance for CUNIT strings: archive files carry 'HZ', 'M/S', 'DEG', 'KM/S' ..."""
+    u = str(unit).strip()
+    if u in table:
+        return u
+    k = folded.get(u.lower())
+    if k is None:
+        raise ValueError("unknown %s unit %r (known: %s)" % (what, unit, ', '.join(sorted(x for x in table if x))))
+    return k
+
+
 def spectral_unit_scale(si_unit, unit):
     """Factor taking a value in the WCS's SI unit to ``unit`` (spectral_axis.py:67-73)."""
     unit = str(unit)
+    unit = _SI_FOLDED.get(unit.strip().lower(), unit) if unit not in _SI else unit
     if unit not in _SI or _SI[unit][0] != si_unit:
         raise ValueError("unit %r is not convertible from %r" % (unit, si_unit))
     return 1.0 / _SI[unit][1]
@@ -36,21 +55,20 @@ class CubeWCS(object):
         cdelt = np.array(cdelt, dtype=np.float64)
         cunit = [str(c) for c in cunit]
         for i in (0, 1):
-            f = _DEG[cunit[i]]
+            f = _DEG[_normalise_unit(cunit[i], _DEG, _DEG_FOLDED, 'celestial')]
             crval[i] *= f
             cdelt[i] *= f
             cunit[i] = 'deg'
-        name, f = _SI[cunit[2]]
+        name, f = _SI[_normalise_unit(cunit[2], _SI, _SI_FOLDED, 'spectral')]
         crval[2] *= f
         cdelt[2] *= f
         cunit[2] = name
         self.crval, self.cdelt, self.cunit = crval, cdelt, cunit
         self.crpix = np.array(crpix, dtype=np.float64)
         self.pc = np.eye(3) if pc is None else np.array(pc, dtype=np.float64)
-        proj = self.ctype[0][-3:]
-        if proj not in ('TAN', 'SIN'):
-            raise NotImplementedError("celestial projection %r (TAN and SIN are supported)" % proj)
-        self.proj = proj
+        # moments, reductions, smoothing and convolve_to never evaluate the projection: any cube can be built and
+        # read; only `reproject` (celestial_params) needs the closed forms the device pixel map implements
+        self.proj = self.ctype[0][-3:]
         if lonpole is None:
             lonpole = 0.0 if self.crval[1] >= 90.0 else 180.0        # FITS paper II, zenithal default
         self.lonpole = float(lonpole)
@@ -64,6 +82,10 @@ class CubeWCS(object):
         crval = [g('CRVAL%d' % i, 0.0) for i in (1, 2, 3)]
         crpix = [g('CRPIX%d' % i, 0.0) for i in (1, 2, 3)]
         cunit = [g('CUNIT%d' % i, 'deg' if i < 3 else '') for i in (1, 2, 3)]
+        if not str(cunit[2]).strip():
+            # a blank CUNIT means the SI unit of the axis type (FITS paper III; what wcslib assumes)
+            base = str(ctype[2] or '')[:4].upper()
+            cunit[2] = {'VRAD': 'm/s', 'VOPT': 'm/s', 'VELO': 'm/s', 'FELO': 'm/s', 'FREQ': 'Hz', 'WAVE': 'm', 'AWAV': 'm'}.get(base, '')
         if any(('CD%d_%d' % (i, j)) in hdr for i in (1, 2, 3) for j in (1, 2, 3)):
             cd = np.array([[g('CD%d_%d' % (i, j), 0.0) for j in (1, 2, 3)] for i in (1, 2, 3)], dtype=np.float64)
             cdelt = [1.0, 1.0, 1.0]
@@ -97,6 +119,8 @@ class CubeWCS(object):
 
     def celestial_params(self):
         """The 12 doubles ``sc_wcs_pixel_map`` takes."""
+        if self.proj not in ('TAN', 'SIN'):
+            raise NotImplementedError("celestial projection %r: the device pixel map implements TAN and SIN" % self.proj)
         m = self.pixel_scale_matrix
         return np.array([self.crpix[0], self.crpix[1], self.crval[0], self.crval[1],
                          m[0, 0], m[0, 1], m[1, 0], m[1, 1], self.lonpole,

@@ -145,3 +145,68 @@ def test_degenerate_stokes_axis_is_dropped(tmp_path):
     io_fits.write_fits(str(tmp_path / 'img.fits'), d2[0], HDR)
     with pytest.raises(io_fits.FITSReadError):
         scb.SpectralCube.read(str(tmp_path / 'img.fits'))               # "Data should be 3- or 4-dimensional"
+
+
+GOLDEN_FITS = __import__('os').path.join(__import__('os').path.dirname(__file__), 'golden', 'example_cube.fits')
+
+
+def test_reference_fixture_header_parses():
+    """tests/golden/example_cube.fits is the reference's own fixture (spectral_cube/tests/data/example_cube.fits,
+    read by tests/test_io.py:16-18 and tests/test_dask.py:240-242): BITPIX -32, NAXIS 3 x 4 x 7 x 1."""
+    with open(GOLDEN_FITS, 'rb') as f:
+        hdr, off = io_fits.read_header(f)
+    assert off == 5760 and hdr['BITPIX'] == -32 and hdr['NAXIS'] == 4
+    assert (hdr['NAXIS1'], hdr['NAXIS2'], hdr['NAXIS3'], hdr['NAXIS4']) == (3, 4, 7, 1)
+    assert hdr['BUNIT'] == 'Jy/beam' and hdr['CTYPE1'] == 'RA---ARC' and hdr['CTYPE3'] == 'VRAD'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_reference_fixture_reads_like_numpy(use_dask):
+    """`SpectralCube.read` (io/fits.py:171-260) of the reference-held file against a plain numpy '>f4' view of its
+    data block: same voxels bit for bit, the degenerate fourth axis dropped, isfinite mask (:214), unit and beam from
+    the header (cube_utils.try_load_beam), both classes alike (tests/test_dask.py:240-252)."""
+    import spectral_cube_b200 as scb
+    want = np.fromfile(GOLDEN_FITS, dtype='>f4', offset=5760, count=3 * 4 * 7).reshape(7, 4, 3).astype(np.float32)
+    cube = scb.SpectralCube.read(GOLDEN_FITS, use_dask=use_dask)
+    assert type(cube) is (scb.DaskSpectralCube if use_dask else scb.SpectralCube)
+    assert cube.shape == (7, 4, 3) and cube.unit == 'Jy/beam'
+    assert np.array_equal(cube._data.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(cube.mask.include(), np.isfinite(want))
+    np.testing.assert_array_equal(cube.filled_data[:], np.where(np.isfinite(want), want, np.nan))
+    assert abs(cube.beam.major - 0.0003467814737101) < 1e-15 and abs(cube.beam.pa - 22.12153897146) < 1e-10
+    # VRAD with a blank CUNIT3 is in m/s: channel i sits at CRVAL3 + CDELT3 (i + 1 - CRPIX3)
+    np.testing.assert_allclose(cube.spectral_axis, 7000.0 - 103.6813929677 * (np.arange(7) + 1 - 77.62811279297), rtol=1e-12)
+    assert np.nanmin(want) == np.float32(-0.0140879265964) and np.nanmax(want) == np.float32(0.01936739496887)   # DATAMIN / DATAMAX
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_masked_cube_is_written_filled(tmp_path, use_dask):
+    """`cube.write` saves `PrimaryHDU(self.unitless_filled_data[:])` (spectral_cube.py:2563-2570, dask :1400-1405):
+    masked voxels reach the file as the fill value, not as the raw data."""
+    import spectral_cube_b200 as scb
+    path, out = str(tmp_path / 'c.fits'), str(tmp_path / 'masked.fits')
+    d = _cube((6, 9, 12), seed=11)
+    io_fits.write_fits(path, d, HDR)
+    cube = scb.SpectralCube.read(path, use_dask=use_dask)
+    masked = cube.with_mask(cube > 0.25)
+    masked.write(out)
+    def data_of(fn):
+        with open(fn, 'rb') as f:
+            hdr, off = io_fits.read_header(f)
+        assert hdr['BITPIX'] == -32
+        return np.fromfile(fn, dtype='>f4', offset=off, count=d.size).reshape(d.shape).astype(np.float32)
+    back = data_of(out)
+    want = np.where(np.isfinite(d) & (d > 0.25), d, np.nan).astype(np.float32)
+    assert np.array_equal(np.isnan(back), np.isnan(want)) and np.isnan(back).sum() > d.size // 3
+    assert np.array_equal(back[~np.isnan(back)], want[~np.isnan(want)])
+    masked.with_fill_value(-7.0).write(out, overwrite=True)
+    back = data_of(out)
+    assert np.array_equal(back, np.where(np.isnan(want), np.float32(-7.0), want))
+    # a reprojected cube holds float64 (reproject_interp's output): the file does too
+    rp = cube.reproject(dict(cube.header))
+    rp.write(out, overwrite=True)
+    with open(out, 'rb') as f:
+        hdr, off = io_fits.read_header(f)
+    assert hdr['BITPIX'] == -64

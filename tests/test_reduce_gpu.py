@@ -193,15 +193,11 @@ def test_reductions_on_views_with_odd_widths():
         assert_maps_close(sub.mean(axis=0).value, osub.mean(axis=0), rtol=1e-5, atol=1e-6)
 
 
-# ---- along the spatial axes: sc_reduce_spatial (opt-in, SC_REDUCE_SPATIAL=1) ------------------------------------
-@pytest.mark.skipif(__import__('os').environ.get('SC_TEST_OPT_IN') != '1',
-                    reason="sc_reduce_spatial is opt-in and has not met hardware yet: set SC_TEST_OPT_IN=1 "
-                           "(tools/gpu_first_call.sh does)")
+# ---- along the spatial axes: sc_reduce_spatial ------------------------------------------------------------------
 @pytest.mark.parametrize('axis', [1, 2])
 @pytest.mark.parametrize('shape,maskname', [((5, 40, 64), 'isfinite'), ((3, 33, 70), 'gt3'), ((2, 7, 13), 'or'),
                                             ((4, 1, 31), 'isfinite'), ((2, 300, 1), 'gt3')])
-def test_reductions_along_the_spatial_axes(shape, maskname, axis, monkeypatch):
-    monkeypatch.setenv('SC_REDUCE_SPATIAL', '1')
+def test_reductions_along_the_spatial_axes(shape, maskname, axis):
     data, sc, oc = _pair(shape, maskname, 'spatial')
     filled = oc._get_filled_data(fill=np.nan).astype(np.float64)
     import warnings
