@@ -92,10 +92,14 @@ GRIDS = {
 
 
 @use_dask
+@pytest.mark.parametrize('kernel', ['direct', 'tma'])
 @pytest.mark.parametrize('flip_in', [False, True])
 @pytest.mark.parametrize('fill_value', [None, -5.0])
 @pytest.mark.parametrize('gridname', sorted(GRIDS))
-def test_spectral_interpolate_matches_oracle(gridname, fill_value, flip_in, use_dask):
+def test_spectral_interpolate_matches_oracle(gridname, fill_value, flip_in, kernel, use_dask, monkeypatch):
+    # both device kernels: the direct one (small / unaligned planes) and `spectral_interp_tma_kernel`, the one every
+    # benchmark shape runs (auto-selected only from 148 row tiles on; forced here through the library's switch)
+    monkeypatch.setenv('SC_INTERP_KERNEL', '1' if kernel == 'direct' else '2')
     data = _random_cube((24, 5, 12), seed=41, nan_frac=0.08)
     w = dict(BENCH_WCS)
     if flip_in:
@@ -118,6 +122,39 @@ def test_spectral_interpolate_matches_oracle(gridname, fill_value, flip_in, use_
     assert_maps_close(gd, wd, rtol=RTOL, atol=1e-12, what=gridname)
     np.testing.assert_array_equal(got.mask.include(), want._mask_include(), err_msg=gridname)
     np.testing.assert_allclose(got.spectral_axis, want.spectral_axis, rtol=1e-12)
+
+
+@use_dask
+@pytest.mark.parametrize('reverse_out', [False, True])
+def test_interpolate_benchmark_block_matches_oracle(use_dask, reverse_out, monkeypatch):
+    """Config 5's interpolation (2048 -> 1024 channels on 4096-wide rows) on an 8-row block of the benchmark cube,
+    through `spectral_interp_tma_kernel`, the kernel the benchmark runs (forced: on its own the library picks it from
+    148 row tiles on, this block has 64), against np.interp / interp1d per spaxel (spectral_cube.py:3298-3315,
+    dask_spectral_cube.py:1342-1364)."""
+    import spectral_cube_b200 as scb
+    from spectral_cube_b200.synth import synth_cube, benchmark_wcs
+    from oracle.synth import synth_block
+    monkeypatch.setenv('SC_INTERP_KERNEL', '2')
+    nchan, ny, nx, nout = 2048, 8, 4096, 1024
+    w = benchmark_wcs(nchan, 4096, nx)
+    wkw = dict(ctype=list(w.ctype), crval=[w.crval[0], w.crval[1], w.crval[2] / 1e3], crpix=list(w.crpix),
+               cdelt=[w.cdelt[0], w.cdelt[1], w.cdelt[2] / 1e3], cunit=['deg', 'deg', 'km/s'])
+    y0 = 98                                           # rows 98 .. 105 straddle the 102-row blank frame
+    dev = synth_cube(nchan, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    host = synth_block(nchan, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), host.view(np.uint32))
+    sc = gpu_cube(dev, wkw, use_dask=use_dask, spectral_unit='km/s')
+    oc = oracle_cube(host, wkw, use_dask=use_dask, spectral_unit='km/s')
+    sa = oc.spectral_axis
+    grid = np.linspace(sa[0], sa[-1], nout)
+    if reverse_out:
+        grid = grid[::-1]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        got = sc.spectral_interpolate(grid, suppress_smooth_warning=True)
+        want = oc.spectral_interpolate(grid, suppress_smooth_warning=True)
+    assert_maps_close(data_of(got), want._data, rtol=RTOL, atol=1e-12, what='c5 block')
+    np.testing.assert_array_equal(got.mask.include(), want._mask_include())
 
 
 def test_interpolate_identity_and_linearity_at_scale():
