@@ -327,7 +327,8 @@ class RowShardedCube(object):
         w = loc._wcs.copy()
         w.crpix[1] += self.y0                                  # back to the full image's WCS
         w.crpix[2] -= c0
-        sub = type(loc)(chan_local, w, unit=loc._unit, fill_value=loc._fill_value, spectral_unit=loc._spectral_unit)
+        sub = type(loc)(chan_local, w, unit=loc._unit, fill_value=loc._fill_value, spectral_unit=loc._spectral_unit,
+                        allow_huge_operations=loc.allow_huge_operations)
         if hasattr(header, 'celestial_params'):
             so = tuple(kw.pop('shape_out'))
             kw['shape_out'] = (c1 - c0,) + so[1:]

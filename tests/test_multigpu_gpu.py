@@ -35,55 +35,8 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
-        import spectral_cube_b200 as scb
-        from spectral_cube_b200 import distributed as D
-        from spectral_cube_b200.synth import synth_cube, benchmark_wcs
-        nchan, ny, nx = 24, 96, 256
-        wcs = benchmark_wcs(nchan, ny, nx)
-        full = synth_cube(nchan, ny, nx, nan_permille=5, border=3)          # every rank can regenerate all of it
-        y0, y1 = D.row_partition(ny, world)[rank]
-        local = synth_cube(nchan, y1 - y0, nx, y0=y0, ny_total=ny, nx_total=nx, nan_permille=5, border=3)
-        assert torch.equal(torch.nan_to_num(local, nan=-1.0), torch.nan_to_num(full[:, y0:y1], nan=-1.0))
-
-        def with_isfinite(c):
-            c._mask = scb.LazyMask(np.isfinite, cube=c)
-            return c
-        whole = with_isfinite(scb.DaskSpectralCube(full, wcs, unit='K'))
-        shard = D.RowShardedCube.from_full_wcs(scb.DaskSpectralCube, local, wcs, ny, unit='K')
-        with_isfinite(shard.local)
-        res = {}
-        # moments: local rows equal the same rows of the whole-cube map, and the gathered map is whole
-        import warnings
-        with warnings.catch_warnings():
-            warnings.simplefilter('ignore')
-            for order in (0, 1, 2):
-                ref = whole.moment(order=order).value
-                got = shard.moment(order=order).value
-                res['moment%d' % order] = bool(np.array_equal(got, ref[y0:y1], equal_nan=True))
-                res['gather%d' % order] = bool(np.array_equal(shard.moment(order=order, gather=True), ref, equal_nan=True))
-        # spatial smooth with halos, both exchange modes
-        k = scb.Gaussian2DKernel(8 / 2.3548200450309493)
-        ref = whole.spatial_smooth(k)._data
-        for mode in ('p2p', 'allgather'):
-            got = shard.spatial_smooth(k, halo_mode=mode).local._data
-            res['spatial_' + mode] = bool(torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref[:, y0:y1], nan=-7.0)))
-        # convolve_to on row shards: both classes, Jy/beam rescale and the convolve_fft rule included
-        pix = float(abs(wcs.cdelt[1]))
-        for cls in (scb.SpectralCube, scb.DaskSpectralCube):
-            w2 = with_isfinite(cls(full, wcs, unit='Jy/beam', beam=scb.Beam(3 * pix)))
-            s2 = D.RowShardedCube.from_full_wcs(cls, local, wcs, ny, unit='Jy/beam', beam=scb.Beam(3 * pix))
-            with_isfinite(s2.local)
-            ref = w2.convolve_to(scb.Beam(5 * pix))._data
-            got = s2.convolve_to(scb.Beam(5 * pix)).local._data
-            res['convolve_to_' + cls.__name__] = bool(torch.equal(torch.nan_to_num(got, nan=-7.0),
-                                                                  torch.nan_to_num(ref[:, y0:y1], nan=-7.0)))
-        # reproject through the row->channel re-shard
-        a = np.radians(30.0)
-        hdr = dict(whole.header)
-        hdr.update({'PC1_1': np.cos(a), 'PC1_2': -np.sin(a), 'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
-        ref = whole.reproject(hdr)._data_hi
-        sub, (c0, c1) = shard.reproject(hdr)
-        res['reproject'] = bool(torch.equal(torch.nan_to_num(sub._data_hi, nan=-7.0), torch.nan_to_num(ref[c0:c1], nan=-7.0)))
+        from spectral_cube_b200.selftest import sharded_parity
+        res = sharded_parity()
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
