@@ -188,6 +188,16 @@ def wcs_kw(ny_total, nx_total, y0=0):
 # (dask's 'processes' scheduler: numpy's masked-array path holds the GIL) maps over them.  The pool is created
 # before the clock starts; the sample is inherited copy-on-write.
 _CPU_SAMPLE = None
+_SYNTH_CACHE = {}
+
+
+def _cached_block(*args, **kw):
+    """oracle.synth.synth_block, memoised: the sample of a config is the same every step."""
+    from oracle.synth import synth_block
+    key = (args, tuple(sorted(kw.items())))
+    if key not in _SYNTH_CACHE:
+        _SYNTH_CACHE[key] = synth_block(*args, **kw)
+    return _SYNTH_CACHE[key]
 
 
 def _cpu_moments_work(i):
@@ -271,10 +281,13 @@ def cpu_sample(config, threads, scale=1.0):
     global _CPU_SAMPLE
     import numpy as np
     from oracle.synth import synth_block
+    # everything the workers use is imported HERE, before the fork: an `import scipy` inside sixteen freshly forked
+    # workers would otherwise sit in the timed window
+    import oracle.cube, oracle.wcs, oracle.convolve, oracle.interp, oracle.reproject, oracle.moments   # noqa: F401,E401
     if config in (1, 3):
         rows = max(threads, int((128 if config == 1 else 32) * scale))
         y0 = NY // 2 - rows // 2
-        data = synth_block(NCHAN, rows, NX, y0=y0, ny_total=NY, nx_total=NX, seed=SEED, nan_permille=1, border=BORDER)
+        data = _cached_block(NCHAN, rows, NX, y0=y0, ny_total=NY, nx_total=NX, seed=SEED, nan_permille=1, border=BORDER)
         nblk = max(1, min(threads, rows))
         bounds = np.linspace(0, rows, nblk + 1).astype(int)
         _CPU_SAMPLE = (data, wcs_kw(NY, NX, y0), bounds)
@@ -287,7 +300,7 @@ def cpu_sample(config, threads, scale=1.0):
         nchan, ny, nx = C4_SHAPE
         h, rows, planes = 14, int(96 * scale), threads
         y0 = ny // 2
-        blk = synth_block(planes, rows + 2 * h, nx, y0=y0 - h, ny_total=ny, nx_total=nx, seed=SEED, nan_permille=1, border=102)
+        blk = _cached_block(planes, rows + 2 * h, nx, y0=y0 - h, ny_total=ny, nx_total=nx, seed=SEED, nan_permille=1, border=102)
         _CPU_SAMPLE = (blk, h)
         dt, n = _timed_pool_map(_cpu_c4_work, planes, threads)
         return planes * rows * nx, dt, ("%d channel planes x rows [%d,%d) of the %dx%dx%d cube (+14 halo rows each side), oracle "
@@ -298,7 +311,7 @@ def cpu_sample(config, threads, scale=1.0):
         nout = 1024
         rows = max(threads, int(16 * scale))
         y0 = ny // 2
-        data = synth_block(nchan, rows, nx, y0=y0, ny_total=ny, nx_total=nx, seed=SEED, nan_permille=1, border=102)
+        data = _cached_block(nchan, rows, nx, y0=y0, ny_total=ny, nx_total=nx, seed=SEED, nan_permille=1, border=102)
         inaxis = -321.214698632 + 1.28821496879 * np.arange(nchan)
         grid = np.linspace(inaxis[0], inaxis[-1], nout)
         bounds = np.linspace(0, rows, min(threads, rows) + 1).astype(int)
@@ -309,15 +322,17 @@ def cpu_sample(config, threads, scale=1.0):
         from oracle.wcs import OWCS
         from oracle import reproject as orep
         planes = threads
-        img = synth_block(2, ny, nx, seed=SEED + 1, nan_permille=1, border=102)       # the workers alternate between two images
+        img = _cached_block(2, ny, nx, seed=SEED + 1, nan_permille=1, border=102)       # the workers alternate between two images
         w_in = OWCS(**wcs_kw(ny, nx))
         a = np.radians(30.0)
         kw = wcs_kw(ny, nx)
         kw['pc'] = [[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]]
         w_out = OWCS(**kw)
-        t0 = time.perf_counter()
-        yin, xin = orep.input_pixel_coords(w_in, w_out, (ny, nx))          # once per cube, like reproject_interp
-        dt_map = time.perf_counter() - t0
+        if 'pixmap' not in _SYNTH_CACHE:
+            t0 = time.perf_counter()
+            pm = orep.input_pixel_coords(w_in, w_out, (ny, nx))            # once per cube, like reproject_interp
+            _SYNTH_CACHE['pixmap'] = pm + (time.perf_counter() - t0,)
+        yin, xin, dt_map = _SYNTH_CACHE['pixmap']
         _CPU_SAMPLE = (img, yin, xin)
         dt_r, n2 = _timed_pool_map(_cpu_c5_reproject_work, planes, threads)
         vox_r = planes * ny * nx
