@@ -56,6 +56,8 @@ struct SpatialParams {
     double tx_scaled[SP_MAX_TAPS];        // tx * 2^896 (the row pass widens float32 by bit placement)
     uint32_t qy[SP_MAX_TAPS], qx[SP_MAX_TAPS];    // round(t * 2^31): the denominator's exact integer factors (sparse kernel)
     unsigned long long qall;              // (sum qy) * (sum qx): the denominator with nothing missing
+    uint32_t cqy[SP_MAX_TAPS + 1];        // prefix sums of qy: cqy[k] = qy[0] + .. + qy[k-1] (pipe kernel, blank blocks)
+    uint32_t cqx[SP_MAX_TAPS + 1];        // prefix sums of qx (pipe kernel, runs of missing inputs in crowded blocks)
     uint32_t qsx;                         // sum qx
     double qscale31;                      // qall * 2^(896-31): out = top * qall / present; reciprocal of present >> 31, widened by bit placement
     float lo_closed, hi_closed;          // interval mask as a closed float32 interval
@@ -671,6 +673,591 @@ sep_sparse_kernel(const __grid_constant__ SpatialParams p) {
     }
 }
 
+// ================================================================================================
+// sep_pipe_kernel -- the separable path as a warp-specialised pipeline (round 2; replaces sep_sparse_kernel).
+//
+// Why: ncu on sep_sparse_kernel showed ~290 thread-instructions per voxel for the 58 DFMAs a 29 x 29 separable
+// kernel needs -- the FP64 pipe (2 issue cycles per DFMA) sat at 27 %.  The budget of an FP64-bound kernel is ONE
+// other instruction per DFMA.  This kernel gets there by (a) 16 outputs per thread in BOTH passes, inputs streamed
+// through registers once (input-outer order: a loaded value feeds up to 16 independent accumulator chains), (b) taps
+// held in registers for the whole march (DFMA with a constant-bank operand issues 10 % slower), (c) no phase
+// barriers: row warps and column warps are different warps that meet through mbarriers on a ring of row-passed
+// blocks, (d) compile-time ring offsets from three base pointers instead of modular index arithmetic, (e) the
+// integer deficit of the denominator kept as a separable quantity: missing inputs scatter qx[.] into a 32-bit row
+// plane with shared-memory atomics (29 per missing input), the column warps fold only the DIRTY rows with qy[.].
+//
+// CTA = one 128-column strip of one channel marching down the rows in blocks of 16; 9 warps:
+//   warp 8      producer: raw rows (strip + 16-column halo) of block b -> raw[b % 2] with cp.async.bulk (TMA);
+//   warps 0-3   row warps: widen the block to float64 once (bit placement, missing -> 0, listed), row pass
+//               (thread = row r, 16-column segment g) -> top[b % 4], row deficits -> rowdef[b % 4];
+//   warps 4-7   column warps: output block b - 1 from ring blocks b - 2 .. b (thread = column), deficit, epilogue, store.
+// One CTA per SM (166 KB of shared memory, up to 224 registers): one row warp and one column warp per scheduler.
+// Denominator semantics are those of sep_sparse_kernel (exact integers, zero padding valid, present == 0 <=> nothing
+// valid); blocks with more than PP_CAP missing inputs compute their row deficits densely, blank blocks in closed form.
+// ================================================================================================
+constexpr int PP_R = 16;                   // rows per block = outputs per thread in both passes
+constexpr int PP_RS = 2;                   // raw ring stages
+constexpr int PP_NB = 4;                   // ring of row-passed blocks
+constexpr int PP_WD = SP_W + 2;            // padded widened row (doubles): the 8 rows of an LDS.128 phase hit 8 bank groups
+constexpr int PP_TOP = SP_TX + 2;          // padded ring row (doubles)
+constexpr int PP_CAP = 64;                 // listed missing inputs per block; more -> dense integer row deficits
+constexpr int PP_FULL = PP_R * SP_W;       // every sample of the block's window missing
+constexpr int PP_GROUP = 128;              // threads per role
+constexpr int PP_THREADS = 2 * PP_GROUP + 32;
+enum { PM_CLEAN = 0, PM_SPARSE = 1, PM_CROWDED = 2, PM_BLANK = 3 };
+
+struct PipeSmem {
+    double top[PP_NB * PP_R][PP_TOP];
+    double wd[2][PP_R][PP_WD];
+    uint32_t rowdef[PP_NB * PP_R][SP_TX];
+    float raw[PP_RS][PP_R][SP_W];
+    uint32_t qyp[96];                      // qy[k] at index k + 32, zero elsewhere (the column warps' deficit fold)
+    uint32_t cqxp[160];                    // cqx[clamp(t - 64, 0, NT)] at index t (runs of missing inputs, crowded blocks)
+    uint32_t rowmask[PP_R][8];             // crowded blocks: bit c of row r = window sample (r, c) is missing (5 words used)
+    uint16_t list[3][PP_CAP];
+    int count[3];
+    int mode[PP_NB];
+    uint32_t dirty[PP_NB][4];              // per 32-column segment: bit r = row r of the block holds non-zero row deficits there
+    uint64_t full[PP_RS], empty[PP_RS], rfull[PP_NB], rempty[PP_NB];
+};
+static_assert(offsetof(PipeSmem, wd) % 16 == 0 && offsetof(PipeSmem, rowdef) % 16 == 0 && offsetof(PipeSmem, raw) % 16 == 0 &&
+              offsetof(PipeSmem, qyp) % 16 == 0, "vector accesses need 16-byte aligned members");
+
+__device__ __forceinline__ void pipe_bar(int id) {          // barrier among the 128 row threads
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(PP_GROUP) : "memory");
+}
+
+// a register copy of a kernel parameter that the compiler cannot fold back into a constant-bank operand
+__device__ __forceinline__ double reg_copy(double v) {
+    double r;
+    asm volatile("mov.b64 %0, %1;" : "=d"(r) : "d"(v));
+    return r;
+}
+
+struct PipeBlock {                         // what the out-of-line paths need to know about the block being processed
+    int64_t c, yblk, x0, xl, xr;
+};
+
+// the filled sample at window position (row, col) of the block: zero outside the image (a valid sample), the
+// neighbouring shard's filled row in the halo, the masked-out value replaced by the fill value
+__device__ __noinline__ float pipe_filled(const SpatialParams &p, const float (*raw)[SP_W], int row, int col, const PipeBlock &k) {
+    const int64_t y = k.yblk + row, x = k.x0 - SP_HP + col;
+    const bool own = y >= 0 && y < p.ny;
+    const bool halo = (y < 0 && p.halo_top && y >= -p.halo_rows) || (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows);
+    float v = 0.0f;
+    if (x >= k.xl && x < k.xr && (own || halo)) {
+        v = raw[row][col];
+        if (own && p.mask.mode != MODE_NONE && !mask_include_rt(p.mask, v, k.c, y, x)) v = p.fill;
+    }
+    return v;
+}
+
+// v * 2^-896 as a double, exactly, for FINITE v (no inf / NaN special case)
+__device__ __forceinline__ double place_scaled_finite(float v) {
+    const int b = __float_as_int(v);
+    return __hiloint2double((b >> 3) & 0x8FFFFFFF, b << 29);
+}
+
+// (1, fast) widen an interior block: 16 rows x 80 pairs, warp w takes rows 4w .. 4w+3; returns the missing-element bits
+template <bool FINITE>
+__device__ __forceinline__ uint32_t pipe_widen_fast(PipeSmem &sm, int s, int par, int warp, int lane, float lo_c, float hi_c) {
+    uint32_t miss = 0u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        // passes 0..7: row 4w + i/2, pairs 32 (i&1) + lane; passes 8, 9: the last 16 pairs of rows 4w + 2(i-8) + (lane>>4)
+        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
+        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+        const float2 v = *reinterpret_cast<const float2 *>(&sm.raw[s][row][2 * pc]);
+        const bool ok0 = (v.x >= lo_c) & (v.x <= hi_c);           // false for NaN
+        const bool ok1 = (v.y >= lo_c) & (v.y <= hi_c);
+        const float w0 = ok0 ? v.x : 0.0f, w1 = ok1 ? v.y : 0.0f;
+        *reinterpret_cast<double2 *>(&sm.wd[par][row][2 * pc]) =
+            FINITE ? make_double2(place_scaled_finite(w0), place_scaled_finite(w1)) : make_double2(place_scaled_sp(w0), place_scaled_sp(w1));
+        miss |= (ok0 ? 0u : 1u << (2 * i)) | (ok1 ? 0u : 2u << (2 * i));
+    }
+    return miss;
+}
+
+// (1, slow) widen a block that touches the image border, halo rows or a mask the interval test cannot express
+__device__ __noinline__ void pipe_widen_slow(const SpatialParams &p, PipeSmem &sm, int s, int par, int l3, int warp, int lane,
+                                             const PipeBlock &k) {
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i) {
+        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
+        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+        const float vx = pipe_filled(p, sm.raw[s], row, 2 * pc, k);
+        const float vy = pipe_filled(p, sm.raw[s], row, 2 * pc + 1, k);
+        const bool ok0 = vx == vx, ok1 = vy == vy;
+        *reinterpret_cast<double2 *>(&sm.wd[par][row][2 * pc]) = make_double2(place_scaled_sp(ok0 ? vx : 0.0f), place_scaled_sp(ok1 ? vy : 0.0f));
+        if (!ok0) { const int idx = atomicAdd(&sm.count[l3], 1); if (idx < PP_CAP) sm.list[l3][idx] = (uint16_t)((row << 8) | (2 * pc)); }
+        if (!ok1) { const int idx = atomicAdd(&sm.count[l3], 1); if (idx < PP_CAP) sm.list[l3][idx] = (uint16_t)((row << 8) | (2 * pc + 1)); }
+    }
+}
+
+// (4) crowded block (more than PP_CAP missing inputs: blank frames, masked regions): the row deficits of one thread's 16
+// outputs from the RUNS of missing inputs in its window -- a run [i0, i1] adds qx[j + 2H - i1] + .. + qx[j + 2H - i0] to output j,
+// two look-ups in the clamped prefix-sum table whatever its length.  Step A (all row threads, then a barrier): per-row missing
+// bits by warp ballot; step B: this thread's 16 + 2H window bits, run by run.
+__device__ __noinline__ void pipe_crowded_masks(const SpatialParams &p, PipeSmem &sm, int s, int warp, int lane,
+                                                bool slow, float lo_c, float hi_c, const PipeBlock &k) {
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+        const int row = 4 * warp + rr;
+#pragma unroll 1
+        for (int q = 0; q < SP_W / 32; ++q) {
+            const int col = 32 * q + lane;
+            const float v = slow ? pipe_filled(p, sm.raw[s], row, col, k) : sm.raw[s][row][col];
+            const unsigned word = __ballot_sync(0xffffffffu, !((v >= lo_c) & (v <= hi_c)));
+            if (lane == 0) sm.rowmask[row][q] = word;
+        }
+        if (lane < 3) sm.rowmask[row][SP_W / 32 + lane] = 0u;
+    }
+}
+
+__device__ __noinline__ void pipe_crowded_rowdef(PipeSmem &sm, int slot, int rrow, int seg, int h) {
+    uint32_t dx[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dx[j] = 0u;
+    const int nin = PP_R + 2 * h;
+    const int w0 = seg * 16 + SP_HP - h;                          // first window column
+    const uint32_t *m = &sm.rowmask[rrow][w0 >> 5];
+    const int sh = w0 & 31;
+    const uint32_t lo = __funnelshift_r(m[0], m[1], sh), hi = __funnelshift_r(m[1], m[2], sh);
+    unsigned long long W = ((unsigned long long)hi << 32 | lo) & ((1ull << nin) - 1ull);
+#pragma unroll 1
+    while (W) {
+        const int i0 = __ffsll((long long)W) - 1;
+        const unsigned long long rest = ~(W >> i0);
+        const int len = __ffsll((long long)rest) - 1;                 // trailing ones of W >> i0 (at least 1, at most 48)
+        const int i1 = i0 + len - 1;
+        W &= ~(((1ull << len) - 1ull) << i0);
+        // sum over i in [i0, i1] of qx[j + 2h - i] = cqx[j + 2h - i0 + 1] - cqx[j + 2h - i1], indices clamped to [0, nt]
+        const uint32_t *hi_t = &sm.cqxp[64 + 2 * h - i0 + 1], *lo_t = &sm.cqxp[64 + 2 * h - i1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dx[j] += hi_t[j] - lo_t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + rrow][seg * 16 + j]) = make_uint4(dx[j], dx[j + 1], dx[j + 2], dx[j + 3]);
+}
+
+template <int H, int OUT64>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
+    if (p.sel && sel_wants_march(p.sel)) return;         // too many missing samples: the convolved denominator is cheaper
+    constexpr int NT = 2 * H + 1;
+    constexpr int NIN = PP_R + 2 * H;                    // inputs of 16 outputs
+    static_assert(H <= SP_HP && H <= PP_R && (H % 2) == 0, "half-width");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem &sm = *reinterpret_cast<PipeSmem *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    int64_t bid = blockIdx.x;
+    const int strip = (int)(bid % p.strips_per_row); bid /= p.strips_per_row;
+    const int chunk = (int)(bid % p.chunks);
+    const int64_t c = bid / p.chunks;
+    const int64_t x0 = (int64_t)strip * SP_TX;
+    const int64_t ya = (int64_t)chunk * p.rows_per_cta;
+    const int64_t yb = min(p.ny, ya + p.rows_per_cta);
+    const int nout_blk = (int)((yb - ya + PP_R - 1) / PP_R);
+    const int nblk = nout_blk + 2;                       // one run-in and one run-out block
+    const int64_t y_first = ya - PP_R;
+
+    const int64_t xl = max((int64_t)0, x0 - SP_HP), xr = min(p.nx, x0 + SP_TX + SP_HP);
+    const int col_off = (int)(xl - (x0 - SP_HP));
+    const uint32_t row_bytes = (uint32_t)(xr - xl) * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < PP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PP_GROUP / 32); }
+        for (int q = 0; q < PP_NB; ++q) { mbar_init(&sm.rfull[q], PP_GROUP / 32); mbar_init(&sm.rempty[q], PP_GROUP / 32); }
+        mbar_fence_init();
+        sm.count[0] = sm.count[1] = sm.count[2] = 0;
+    }
+    if (tid < 96) { const int k = tid - 32; sm.qyp[tid] = (k >= 0 && k < NT) ? p.qy[k] : 0u; }
+    if (tid >= 96 && tid < 256) { const int t = tid - 96, k = t - 64; sm.cqxp[t] = p.cqx[k < 0 ? 0 : (k > NT ? NT : k)]; }
+    // the columns of the raw rows that lie outside the image are never written by the copies: valid zeros, set once
+    if (col_off > 0 || (int)(xr - xl) < SP_W) {
+        for (int i = tid; i < PP_RS * PP_R * SP_W; i += PP_THREADS) {
+            const int col = i % SP_W;
+            if (col < col_off || col >= col_off + (int)(xr - xl)) (&sm.raw[0][0][0])[i] = 0.0f;
+        }
+    }
+    __syncthreads();
+
+    if (warp == 2 * PP_GROUP / 32) {
+        // ---------------- producer warp ----------------
+        const uint64_t pol = l2_evict_first_policy();
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b % PP_RS;
+            if (b >= PP_RS) mbar_wait(&sm.empty[s], ((b / PP_RS) - 1) & 1);
+            const float *src = nullptr;
+            if (lane < PP_R) {
+                const int64_t y = y_first + (int64_t)b * PP_R + lane;
+                if (y >= 0 && y < p.ny) src = p.in + c * p.stride_c + y * p.stride_y + xl;
+                else if (y < 0 && p.halo_top && y >= -p.halo_rows)
+                    src = p.halo_top + (c * p.halo_rows + (p.halo_rows + y)) * p.nx + xl;
+                else if (y >= p.ny && p.halo_bot && y < p.ny + p.halo_rows)
+                    src = p.halo_bot + (c * p.halo_rows + (y - p.ny)) * p.nx + xl;
+            }
+            const unsigned have = __ballot_sync(0xffffffffu, src != nullptr);
+            if (have != 0xFFFFu) {
+                // rows above / below the image (and no neighbouring shard): zero padding, written here with plain stores
+                for (int r = 0; r < PP_R; ++r) {
+                    if ((have >> r) & 1u) continue;
+                    for (int q = lane; q < SP_W / 4; q += 32) *reinterpret_cast<float4 *>(&sm.raw[s][r][4 * q]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)__popc(have) * row_bytes);      // (release: orders the zero rows too)
+            __syncwarp();
+            if (src) tma_load_1d(&sm.raw[s][lane][col_off], src, row_bytes, &sm.full[s], pol);
+        }
+        return;
+    }
+
+    const bool strip_clipped = xl != x0 - SP_HP || xr != x0 + SP_TX + SP_HP;
+    const bool mask_by_sweep = p.mask.mode == MODE_GENERIC || (p.mask.mode == MODE_INTERVAL && p.fill == p.fill);
+    // zero padding is a VALID sample: the fast path's interval test may run over it only if the interval contains 0
+    const bool zero_ok = p.mask.mode != MODE_INTERVAL || (p.lo_closed <= 0.0f && p.hi_closed >= 0.0f);
+
+    if (warp < PP_GROUP / 32) {
+        // ================= row warps =================
+        const int t = tid;                               // 0 .. 127
+        const int rrow = t & 15, seg = t >> 4;
+        double T[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) T[k] = reg_copy(p.tx_scaled[k]);
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b % PP_RS, par = b & 1, l3 = b % 3, slot = b % PP_NB;
+            PipeBlock blk;
+            blk.c = c; blk.yblk = y_first + (int64_t)b * PP_R; blk.x0 = x0; blk.xl = xl; blk.xr = xr;
+            const bool rows_inside = blk.yblk >= (p.halo_top ? -(int64_t)p.halo_rows : 0) &&
+                                     blk.yblk + PP_R <= p.ny + (p.halo_bot ? (int64_t)p.halo_rows : 0);
+            const bool slow = mask_by_sweep || ((strip_clipped || !rows_inside) && !zero_ok);     // uniform per block
+            float lo_c = -INFINITY, hi_c = INFINITY;
+            if (!slow && p.mask.mode == MODE_INTERVAL) { lo_c = p.lo_closed; hi_c = p.hi_closed; }
+            if (t == 0) sm.count[(b + 1) % 3] = 0;       // last read two blocks ago, next written after this block's barrier
+            mbar_wait(&sm.full[s], (b / PP_RS) & 1);
+
+            // ---- (1) widen every input once: 16 rows x 80 pairs; warp w takes rows 4w .. 4w+3 ----
+            if (slow) {
+                pipe_widen_slow(p, sm, s, par, l3, warp, lane, blk);
+            } else {
+                // bit 2i + e of `miss`: element e of this thread's pair i is missing (listed after the loop: the common
+                // iteration is branch-free).  Under an interval mask the bounds are finite, so +-inf is "missing" and the
+                // placement needs no special case for it.
+                uint32_t miss = 0u;
+                if (p.mask.mode == MODE_INTERVAL) miss = pipe_widen_fast<true>(sm, s, par, warp, lane, lo_c, hi_c);
+                else                              miss = pipe_widen_fast<false>(sm, s, par, warp, lane, lo_c, hi_c);
+                if (__ballot_sync(0xffffffffu, miss != 0u)) {           // warp-uniform: ONE atomic per warp whatever the count
+                    const int n = __popc(miss);
+                    int incl = n;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&sm.count[l3], incl);
+                    int idx = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+                    while (miss && idx < PP_CAP) {
+                        const int bit = __ffs((int)miss) - 1;
+                        miss &= miss - 1u;
+                        const int i = bit >> 1;
+                        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
+                        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+                        sm.list[l3][idx++] = (uint16_t)((row << 8) | (2 * pc + (bit & 1)));
+                    }
+                }
+            }
+            pipe_bar(1);
+            const int cnt = sm.count[l3];                // uniform
+            const int mode = cnt == 0 ? PM_CLEAN : cnt == PP_FULL ? PM_BLANK : cnt <= PP_CAP ? PM_SPARSE : PM_CROWDED;
+            if (mode != PM_CROWDED) {                    // (a crowded block re-reads the raw rows for its dense deficits)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+            }
+            if (b >= PP_NB) mbar_wait(&sm.rempty[slot], ((b / PP_NB) - 1) & 1);
+            if (t < 4) sm.dirty[slot][t] = mode == PM_CROWDED ? 0xFFFFu : 0u;
+            if (t == 4) sm.mode[slot] = mode;
+
+            // ---- (2) sparse block: scatter the listed inputs' qx[.] into the (zeroed) row-deficit plane ----
+            if (mode == PM_SPARSE) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + 4 * i + (t >> 5)][4 * (t & 31)]) = make_uint4(0u, 0u, 0u, 0u);
+                pipe_bar(2);
+                for (int e = warp; e < cnt; e += PP_GROUP / 32) {
+                    const int ent = sm.list[l3][e];
+                    const int r_in = ent >> 8, cin = ent & 255;
+                    const int xo0 = cin - SP_HP - H;                       // out(xo) reads in(xo + H - k): xo = xo0 + k
+                    for (int k = lane; k < NT; k += 32) {
+                        const int xo = xo0 + k;
+                        if (xo >= 0 && xo < SP_TX) atomicAdd(&sm.rowdef[slot * PP_R + r_in][xo], p.qx[k]);
+                    }
+                    if (lane < 2) {                                        // the one or two 32-column segments the taps reach
+                        const int xe = lane == 0 ? max(xo0, 0) : min(xo0 + NT - 1, SP_TX - 1);
+                        if (xo0 + NT - 1 >= 0 && xo0 < SP_TX) atomicOr(&sm.dirty[slot][xe >> 5], 1u << r_in);
+                    }
+                }
+            }
+
+            // ---- (3) row pass: 16 adjacent outputs of row `rrow` from 16 + 2H widened inputs ----
+            double *trow = &sm.top[slot * PP_R + rrow][seg * 16];
+            if (mode == PM_BLANK) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(0.0, 0.0);
+            } else {
+                const double2 *src = reinterpret_cast<const double2 *>(&sm.wd[par][rrow][seg * 16 + SP_HP - H]);
+                double acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int q = 0; q < NIN / 2; ++q) {
+                    const double2 v2 = src[q];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double v = e ? v2.y : v2.x;
+                        const int i = 2 * q + e;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = j + 2 * H - i;                   // out(j) reads in(j + 2H - k) of the window
+                            if (k >= 0 && k < NT) acc[j] = fma(T[k], v, acc[j]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(acc[j], acc[j + 1]);
+            }
+            if (mode == PM_CROWDED) {
+                pipe_crowded_masks(p, sm, s, warp, lane, slow, lo_c, hi_c, blk);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+                pipe_bar(2);
+                pipe_crowded_rowdef(sm, slot, rrow, seg, H);
+                pipe_bar(3);                             // (the masks are rewritten by the next crowded block)
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.rfull[slot]);
+        }
+        return;
+    }
+
+    // ================= column warps =================
+    {
+        const int ccol = tid - PP_GROUP;                 // 0 .. 127
+        const int cw = ccol >> 5;                        // this warp's 32-column segment
+        const int64_t x = x0 + ccol;
+        const bool pass = p.passthrough && p.passthrough[c];
+        double T[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) T[k] = reg_copy(p.ty[k]);
+        const float inv_q = 1.0f / (float)(uint32_t)(p.qall >> 31);
+        const float qall_f = __ull2float_rn(p.qall);
+        const double *topf = &sm.top[0][0];
+        const uint32_t *rdf = &sm.rowdef[0][0];
+        for (int b = 0; b < nblk; ++b) {
+            mbar_wait(&sm.rfull[b % PP_NB], (b / PP_NB) & 1);
+            if (b < 2) continue;
+            // ring blocks of the window: tb = 0, 1, 2 <-> march blocks b - 2, b - 1, b
+            const int s0 = (b - 2) % PP_NB, s1 = (b - 1) % PP_NB, s2 = b % PP_NB;
+            const int m0 = sm.mode[s0], m1 = sm.mode[s1], m2 = sm.mode[s2];          // uniform
+            const int64_t yout = y_first + (int64_t)(b - 1) * PP_R;
+            const int nlive = (int)min((int64_t)PP_R, yb - yout);
+            const bool all_blank = m0 == PM_BLANK && m1 == PM_BLANK && m2 == PM_BLANK;
+
+            // ---- numerators: 16 vertically adjacent outputs from 16 + 2H ring rows (window row i <-> row yout - H + i) ----
+            double acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            if (!all_blank) {
+                // element offsets of the three blocks' first rows in this thread's column (integers: the loads stay LDS)
+                const int o0 = s0 * PP_R * PP_TOP + ccol, o1 = s1 * PP_R * PP_TOP + ccol, o2 = s2 * PP_R * PP_TOP + ccol;
+#pragma unroll
+                for (int i = 0; i < NIN; ++i) {
+                    const int rel = PP_R - H + i;                          // row relative to the first row of block b - 2
+                    const int ob = rel < PP_R ? o0 : rel < 2 * PP_R ? o1 : o2;
+                    const double v = topf[ob + (rel % PP_R) * PP_TOP];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = j + 2 * H - i;
+                        if (k >= 0 && k < NT) acc[j] = fma(T[k], v, acc[j]);
+                    }
+                }
+            }
+
+            // ---- deficits: exact integers; only the rows that are dirty in this warp's 32 columns are folded in ----
+            unsigned long long def[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) def[j] = 0ull;
+            bool any_def = false;                                          // uniform
+            unsigned long long dirty48 = 0ull;                             // bit 16 tb + r: ring row r of block tb
+#pragma unroll
+            for (int tb = 0; tb < 3; ++tb) {
+                const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
+                const int st = tb == 0 ? s0 : tb == 1 ? s1 : s2;
+                if (mt == PM_BLANK) {
+                    any_def = true;
+                    // every row of the block contributes (sum of qx) x qy[k]: prefix sums of qy give the block's share
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // rows rel = 16 tb .. 16 tb + 15 <-> window rows i = rel - (16 - H) <-> k = j + 2H - i
+                        const int khi = j + 2 * H - (PP_R * tb - (PP_R - H));              // k of the block's first row
+                        const int klo = khi - (PP_R - 1);                                   // k of its last row
+                        const int a = klo < 0 ? 0 : (klo > NT ? NT : klo), e = khi + 1 < 0 ? 0 : (khi + 1 > NT ? NT : khi + 1);
+                        if (e > a) def[j] += (unsigned long long)(p.cqy[e] - p.cqy[a]) * p.qsx;
+                    }
+                } else if (mt != PM_CLEAN) {
+                    dirty48 |= (unsigned long long)sm.dirty[st][cw] << (16 * tb);
+                }
+            }
+            // window rows i = rel - (16 - H), i in [0, NIN)
+            unsigned long long todo = (dirty48 >> (PP_R - H)) & ((1ull << NIN) - 1ull);
+            any_def |= todo != 0ull;
+            if (__popcll(todo) > 10) {
+                // crowded neighbourhood: every row of the non-clean blocks, unrolled (compile-time taps, no loop overhead);
+                // rows of sparse blocks that nothing was scattered into hold zeros
+#pragma unroll
+                for (int tb = 0; tb < 3; ++tb) {
+                    const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
+                    const int st = tb == 0 ? s0 : tb == 1 ? s1 : s2;
+                    if (mt != PM_SPARSE && mt != PM_CROWDED) continue;
+                    const int ord = st * PP_R * SP_TX + ccol;
+#pragma unroll
+                    for (int r_in = 0; r_in < PP_R; ++r_in) {
+                        const int i = PP_R * tb + r_in - (PP_R - H);       // window row
+                        if (i < 0 || i >= NIN) continue;
+                        const uint32_t d = rdf[ord + r_in * SP_TX];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = j + 2 * H - i;
+                            if (k >= 0 && k < NT) def[j] += (unsigned long long)d * p.qy[k];
+                        }
+                    }
+                }
+                todo = 0ull;
+            }
+#pragma unroll 1
+            while (todo) {
+                const int i = __ffsll((long long)todo) - 1;                // uniform
+                todo &= todo - 1ull;
+                const int rel = i + PP_R - H;
+                const int st = (b - 2 + (rel >> 4)) % PP_NB;
+                const uint32_t d = rdf[(st * PP_R + (rel & 15)) * SP_TX + ccol];
+                const uint32_t *q = &sm.qyp[32 + 2 * H - i];               // q[j] = qy[j + 2H - i], zero outside the kernel
+#pragma unroll
+                for (int j = 0; j < 16; ++j) def[j] += (unsigned long long)d * q[j];
+            }
+
+            // ---- epilogue: out = top * qall / present ----
+            char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
+            const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
+            if (x < p.nx) {
+                if (!any_def && !pass) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < nlive) {
+                            if (OUT64) *reinterpret_cast<double *>(op + j * ostep) = acc[j];
+                            else       *reinterpret_cast<float *>(op + j * ostep) = (float)acc[j];
+                        }
+                    }
+                } else if (OUT64) {
+#pragma unroll 1
+                    for (int j0 = 0; j0 < 16; j0 += 1) {
+                        // (float64 output is the rarely used form: compact, register arrays indexed through a switch-free select chain)
+                        double a = 0.0; unsigned long long dj = 0ull;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (j == j0) { a = acc[j]; dj = def[j]; }
+                        if (j0 < nlive) {
+                            const unsigned long long present = p.qall - dj;
+                            const uint32_t hi = (uint32_t)(present >> 31);
+                            double res;
+                            if (hi < (1u << 24) || pass) res = sparse_rare_output(p, a, present, pass, c, yout + j0, x);
+                            else res = dj != 0ull ? a * (place_scaled_sp(__frcp_rn((float)hi)) * p.qscale31) : a;
+                            *reinterpret_cast<double *>(op + j0 * ostep) = res;
+                        }
+                    }
+                } else {
+                    // float32 output.  Common case: x = deficit / qall from the top 32 bits (2^-31 of the kernel sum) and
+                    // out = top / (1 - x) in float32 (relative error < 5e-7 while x <= 1/2).  More than half of the weight
+                    // missing: out = top * qall / present with `present` converted from its 64 bits (same accuracy however
+                    // small it is).  Nothing valid at all (present == 0, common inside blank regions) or a plane that is
+                    // copied through: the filled input, fetched in a loop of its own -- it needs neither `acc` nor `def`.
+                    uint32_t rare = 0u;
+                    float *o32 = reinterpret_cast<float *>(op);
+                    if (all_blank || pass) {
+                        rare = 0xFFFFu;                                    // (every deficit equals qall there)
+                    } else if (nlive == PP_R) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float xdef = (float)(uint32_t)(def[j] >> 31) * inv_q;
+                            rare |= xdef > 0.5f ? 1u << j : 0u;
+                            *o32 = __fdividef((float)acc[j], 1.0f - xdef);
+                            o32 += p.out_stride_y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float xdef = (float)(uint32_t)(def[j] >> 31) * inv_q;
+                            rare |= xdef > 0.5f ? 1u << j : 0u;
+                            if (j < nlive) *o32 = __fdividef((float)acc[j], 1.0f - xdef);
+                            o32 += p.out_stride_y;
+                        }
+                    }
+                    rare &= (1u << nlive) - 1u;
+                    if (rare == (1u << nlive) - 1u) {
+                        // every output of this thread is flagged: inside a blank region (or a plane copied through) nothing at
+                        // all is valid under the kernel and the result is the filled input -- 16 INDEPENDENT loads, not a
+                        // chain of them (the loop below waits a full memory latency per output)
+                        bool nothing = true;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) nothing &= def[j] == p.qall;
+                        if (nothing || pass) {
+                            const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
+                            float cv[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) cv[j] = j < nlive ? __ldg(ip + j * p.stride_y) : 0.0f;
+                            float *o = reinterpret_cast<float *>(op);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < nlive) {
+                                    if (!mask_include_rt(p.mask, cv[j], c, yout + j, x)) cv[j] = p.fill;
+                                    o[j * p.out_stride_y] = cv[j];
+                                }
+                            }
+                            rare = 0u;
+                        }
+                    }
+                    if (rare) {
+                        // out of the common path (edges of blank regions): the values move to thread-local arrays so that the
+                        // loop over the flagged outputs can index them
+                        float fa[16];
+                        unsigned long long dd[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { fa[j] = (float)acc[j]; dd[j] = def[j]; }
+                        const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
+                        float *o = reinterpret_cast<float *>(op);
+#pragma unroll 1
+                        while (rare) {
+                            const int j0 = __ffs((int)rare) - 1;
+                            rare &= rare - 1u;
+                            const unsigned long long present = p.qall - dd[j0];
+                            float r;
+                            if (present == 0ull || pass) {
+                                r = __ldg(ip + j0 * p.stride_y);
+                                if (!mask_include_rt(p.mask, r, c, yout + j0, x)) r = p.fill;
+                            } else {
+                                r = fa[j0] * __fdividef(qall_f, __ull2float_rn(present));
+                            }
+                            o[j0 * p.out_stride_y] = r;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.rempty[s0]);
+        }
+    }
+}
+
 // ---- direct 2-D kernel: any odd x odd taps ------------------------------------------------------------
 struct DirectParams {
     SpatialParams sp;
@@ -941,6 +1528,28 @@ static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cuda
     return cudaGetLastError();
 }
 
+template <int H, int OUT64>
+static cudaError_t launch_pipe_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    auto kern = sep_pipe_kernel<H, OUT64>;
+    const size_t smem = sizeof(PipeSmem);
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
+    kern<<<grid, PP_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int OUT64>
+static cudaError_t launch_pipe_h(const SpatialParams &p, int h, unsigned grid, cudaStream_t s) {
+    if (h <= 2)  return launch_pipe_one<2, OUT64>(p, grid, s);
+    if (h <= 4)  return launch_pipe_one<4, OUT64>(p, grid, s);
+    if (h <= 6)  return launch_pipe_one<6, OUT64>(p, grid, s);
+    if (h <= 8)  return launch_pipe_one<8, OUT64>(p, grid, s);
+    if (h <= 10) return launch_pipe_one<10, OUT64>(p, grid, s);
+    if (h <= 12) return launch_pipe_one<12, OUT64>(p, grid, s);
+    if (h <= 14) return launch_pipe_one<14, OUT64>(p, grid, s);
+    return launch_pipe_one<16, OUT64>(p, grid, s);
+}
+
 template <int OUT64>
 static cudaError_t launch_sparse_h(const SpatialParams &p, int h, unsigned grid, cudaStream_t s) {
     if (h <= 2)  return launch_sparse_one<2, OUT64>(p, grid, s);
@@ -1048,7 +1657,8 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
     if (rc) return rc;
     const bool aligned = ((uintptr_t)in % 16 == 0) && stride_c % 4 == 0 && stride_y % 4 == 0 && nx % 4 == 0 &&
                          (!halo_top || (uintptr_t)halo_top % 16 == 0) && (!halo_bot || (uintptr_t)halo_bot % 16 == 0);
-    const int choice = env_int("SC_SPATIAL_KERNEL", 0);          // 0 auto, 1 direct, 2 march
+    // 0 auto (pipe kernel or, for heavily masked cubes, march), 1 direct, 3 march, 4 the round-1 sparse kernel, 5 pipe
+    const int choice = env_int("SC_SPATIAL_KERNEL", 0);
     if (h <= 16 && aligned && choice != 1) {
         const int H = h <= 2 ? 2 : h <= 4 ? 4 : h <= 6 ? 6 : h <= 8 ? 8 : h <= 10 ? 10 : h <= 12 ? 12 : h <= 14 ? 14 : 16;
         double ksy = 0.0, ksx = 0.0;
@@ -1065,7 +1675,7 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
         while (base * chunks < 148 * 4 && ny / (chunks * 2) >= 8 * h + 16) chunks *= 2;
         const int forced = env_int("SC_SPATIAL_CHUNKS", 0);
         if (forced > 0) chunks = forced;
-        p.rows_per_cta = (int)(cdiv(cdiv(ny, chunks), SP_R) * SP_R);
+        p.rows_per_cta = (int)(cdiv(cdiv(ny, chunks), PP_R) * PP_R);     // (a multiple of both kernels' block heights)
         p.chunks = (int)cdiv(ny, p.rows_per_cta);
         const int64_t grid = base * p.chunks;
         SC_CHECK_ARG(grid < ((int64_t)1 << 31), "grid too large");
@@ -1079,6 +1689,8 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
             qsy += p.qy[k]; qsx += p.qx[k];
         }
         nonneg = nonneg && qsy < (1ull << 32) && qsx < (1ull << 32) && qsy > 0 && qsx > 0;
+        p.cqy[0] = p.cqx[0] = 0u;
+        for (int k = 0; k < SP_MAX_TAPS; ++k) { p.cqy[k + 1] = p.cqy[k] + p.qy[k]; p.cqx[k + 1] = p.cqx[k] + p.qx[k]; }   // (wrap only when !nonneg: unused then)
         p.qall = qsy * qsx;
         p.qsx = (uint32_t)qsx;
         p.qscale31 = ldexp((double)p.qall, 896 - 31);
@@ -1098,8 +1710,10 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
         }
         LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
         cudaError_t e = cudaSuccess;
-        if (nonneg && choice != 3)
+        if (nonneg && choice == 4)
             e = out_dtype == SC_F64 ? launch_sparse_h<1>(p, H, (unsigned)grid, s) : launch_sparse_h<0>(p, H, (unsigned)grid, s);
+        else if (nonneg && choice != 3)
+            e = out_dtype == SC_F64 ? launch_pipe_h<1>(p, H, (unsigned)grid, s) : launch_pipe_h<0>(p, H, (unsigned)grid, s);
         if (e == cudaSuccess && (!nonneg || choice == 3 || p.sel))
             e = out_dtype == SC_F64 ? launch_sep_h<1>(p, H, (unsigned)grid, s) : launch_sep_h<0>(p, H, (unsigned)grid, s);
         if (e != cudaSuccess) return cuda_fail(e, "separable spatial kernel launch");

@@ -32,8 +32,17 @@ def sharded_parity(group=None, rows_per_rank=48):
         c._mask = LazyMask(np.isfinite, cube=c)
         return c
 
-    def same(a, b):
-        return bool(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)))
+    detail = {}
+
+    def same(a, b, name=None):
+        ok = bool(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)))
+        if not ok and name is not None:
+            a64, b64 = a.double(), b.double()
+            nan_differs = int((torch.isnan(a64) != torch.isnan(b64)).sum().item())
+            d = torch.nan_to_num(a64 - b64, nan=0.0).abs()
+            rows = torch.nonzero(d.amax(dim=(0, 2)) > 0).flatten().tolist()
+            detail[name] = 'rank %d: %d NaN mismatches, max |diff| %.3g, local rows %s' % (rank, nan_differs, float(d.max().item()), rows[:12])
+        return ok
 
     whole = with_isfinite(DaskSpectralCube(full, wcs, unit='K', allow_huge_operations=True))
     shard = D.RowShardedCube.from_full_wcs(DaskSpectralCube, local, wcs, ny, unit='K', allow_huge_operations=True)
@@ -49,7 +58,7 @@ def sharded_parity(group=None, rows_per_rank=48):
         ref = whole.spatial_smooth(k)._data
         for mode in ('p2p', 'allgather'):
             got = shard.spatial_smooth(k, halo_mode=mode).local._data
-            res['spatial_' + mode] = same(got, ref[:, y0:y1])
+            res['spatial_' + mode] = same(got, ref[:, y0:y1], 'spatial_' + mode)
         pix = float(abs(wcs.cdelt[1]))
         for cls in (SpectralCube, DaskSpectralCube):
             w2 = with_isfinite(cls(full, wcs, unit='Jy/beam', beam=Beam(3 * pix), allow_huge_operations=True))
@@ -58,13 +67,14 @@ def sharded_parity(group=None, rows_per_rank=48):
             with_isfinite(s2.local)
             ref = w2.convolve_to(Beam(5 * pix))._data
             got = s2.convolve_to(Beam(5 * pix)).local._data
-            res['convolve_to_' + cls.__name__] = same(got, ref[:, y0:y1])
+            res['convolve_to_' + cls.__name__] = same(got, ref[:, y0:y1], 'convolve_to_' + cls.__name__)
         a = np.radians(30.0)
         hdr = dict(whole.header)
         hdr.update({'PC1_1': np.cos(a), 'PC1_2': -np.sin(a), 'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
         ref = whole.reproject(hdr)._data_hi
         sub, (c0, c1) = shard.reproject(hdr)
-        res['reproject'] = same(sub._data_hi, ref[c0:c1])
+        res['reproject'] = same(sub._data_hi, ref[c0:c1], 'reproject')
+    res['_detail'] = detail
     return res
 
 
@@ -72,7 +82,7 @@ def all_ranks_agree(res, group=None):
     """AND of every entry over the ranks: (ok, names that failed on some rank)."""
     import torch
     import torch.distributed as dist
-    names = sorted(res)
+    names = sorted(n for n in res if not n.startswith('_'))
     t = torch.tensor([1 if res[n] else 0 for n in names], dtype=torch.int32, device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     flags = t.cpu().tolist()

@@ -1,5 +1,6 @@
-"""spatial_smooth on the kinds of shards config 4 produces, sparse-denominator kernel against the
-convolved-denominator one (GPU box only; scratch tool)."""
+"""spatial_smooth on the kinds of shards config 4 produces: the pipelined kernel (round 2), the round-1 sparse kernel and
+the convolved-denominator kernel (GPU box only; scratch tool).  `python tools/time_spatial_cases.py one` runs the clean
+shard once per kernel (for ncu)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -24,14 +25,23 @@ cases = (("clean shard, 0.1 % NaNs", dict(border=0), False),
          ("top shard of config 4 (102 blank rows + blank side columns)", dict(y0=0, ny_total=4096, nx_total=4096, border=102), False),
          ("interior shard of config 4 (blank side columns)", dict(y0=1024, ny_total=4096, nx_total=4096, border=102), False),
          ("masked > 3 sigma (crowded everywhere)", dict(border=0), True))
+if len(sys.argv) > 1 and sys.argv[1] in ('one', 'one_interior'):
+    dev = synth_cube(nchan, ny, nx, border=0) if sys.argv[1] == 'one' else synth_cube(nchan, ny, nx, y0=1024, ny_total=4096, nx_total=4096, border=102)
+    c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit="K")
+    c._mask = scb.LazyMask(np.isfinite, cube=c)
+    os.environ["SC_SPATIAL_KERNEL"] = "5"
+    for _ in range(3):
+        c._run_spatial_smooth(k.array, _lib.F32)
+    torch.cuda.synchronize()
+    sys.exit(0)
 for name, kw, masked in cases:
     dev = synth_cube(nchan, ny, nx, **kw)
     c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit="K")
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     if masked:
         c = c.with_mask(c > 3.0)
-    for choice in ("0", "2", "3"):
+    for choice in ("0", "5", "4", "3"):
         os.environ["SC_SPATIAL_KERNEL"] = choice
         ms = timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32))
-        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "2": "sparse", "3": "march "}[choice], ms), flush=True)
+        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "5": "pipe  ", "4": "sparse(r1)", "3": "march "}[choice], ms), flush=True)
     del dev, c
