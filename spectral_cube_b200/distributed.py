@@ -227,7 +227,8 @@ class RowShardedCube(object):
         if loc._mask is None:
             return None
         inc = loc._mask._include_tensor(loc._data)
-        blank = (~inc.reshape(inc.shape[0], -1).any(dim=1)).to(torch.int32)
+        # (`.any()` of a uint8 tensor is a uint8 tensor, and `~` of that is a bitwise complement: go through bool)
+        blank = (~inc.bool().reshape(inc.shape[0], -1).any(dim=1)).to(torch.int32)
         if self._is_sharded():
             _dist().all_reduce(blank, op=_dist().ReduceOp.MIN, group=self.group)
         return blank.to(torch.uint8)

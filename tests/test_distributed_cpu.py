@@ -167,6 +167,14 @@ def _sharded_smoothing_job(rank, world):
             ok &= type(out.local) is cls and out.y0 == y0
             sm = sh.spatial_smooth(S.Gaussian2DKernel(1.0), raise_error_jybm=False, halo_mode='allgather')
             ok &= sm.local.beam == sh.local.beam
+            # job-wide blank planes: plane 1 includes nothing on any rank, plane 2 nothing on rank 0 only -> flags 0, 1, 0
+            # exactly (a uint8 `any()` followed by `~` once made every plane "blank": the Jy/beam rescale was skipped)
+            inc = torch.ones((3, y1 - y0, 64), dtype=torch.uint8)
+            inc[1] = 0
+            if rank == 0:
+                inc[2] = 0
+            sh.local._mask._include_tensor = lambda data=None, _inc=inc: _inc
+            ok &= sh._blank_planes().tolist() == [0, 1, 0]
     return bool(ok) and len(calls) > 8
 
 
