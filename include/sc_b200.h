@@ -268,6 +268,14 @@ int sc_scale(void *data, int dtype, int64_t nchan, int64_t ny, int64_t nx,
              int64_t stride_c, int64_t stride_y, double factor, int nan_to_zero,
              const uint8_t *skip_planes, void *stream);
 
+/* mosaic_cubes (cube_utils.py:791-856), the elementwise steps around the per-cube `reproject` calls, contiguous
+ * (nchan, ny, nx) buffers.  sc_mosaic_accumulate: acc += nan_to_num(reprojected) (:838-841) and, when `weight` is given,
+ * weight += footprint0 -- the reprojected cube's mask in channel 0, the 2-D coverage count of :834-836.
+ * sc_mosaic_normalize: acc[c] /= weight for every channel (:847-849), IEEE division like numpy's. */
+int sc_mosaic_accumulate(double *acc, double *weight, const void *reprojected, int dtype, const uint8_t *footprint0,
+                         int64_t nchan, int64_t ny, int64_t nx, void *stream);
+int sc_mosaic_normalize(double *acc, const double *weight, int64_t nchan, int64_t ny, int64_t nx, void *stream);
+
 /* Write the FILLED edge rows a neighbour needs: rows [row0, row0+nrows) of every channel,
  * mask applied (excluded -> fill), into a contiguous (nchan, nrows, nx) float32 buffer. */
 int sc_pack_filled_rows(const float *in, int64_t nchan, int64_t ny, int64_t nx,

@@ -15,6 +15,7 @@ from .masks import (MaskBase, InvertedMask, CompositeMask, BooleanArrayMask, Laz
                     LazyComparisonMask, FunctionMask)
 from .projection import Projection
 from .wcs import CubeWCS
+from .mosaic import mosaic_cubes, combine_headers, find_optimal_celestial_wcs
 from .kernels import (Kernel1D, Kernel2D, Gaussian1DKernel, Gaussian2DKernel, Tophat2DKernel,
                       Box1DKernel, CustomKernel)
 
@@ -25,4 +26,5 @@ __all__ = ['SpectralCube', 'DaskSpectralCube', 'BaseSpectralCube', 'Projection',
            'Kernel1D', 'Kernel2D', 'Gaussian1DKernel', 'Gaussian2DKernel', 'Tophat2DKernel',
            'Box1DKernel', 'CustomKernel', 'VaryingResolutionSpectralCube',
            'DaskVaryingResolutionSpectralCube', 'Beam', 'Beams', 'BeamError', 'NoBeamError', 'BeamWarning',
-           'NonFiniteBeamsWarning', 'EllipticalGaussian2DKernel']
+           'NonFiniteBeamsWarning', 'EllipticalGaussian2DKernel', 'mosaic_cubes', 'combine_headers',
+           'find_optimal_celestial_wcs']

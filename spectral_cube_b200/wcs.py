@@ -159,10 +159,72 @@ class CubeWCS(object):
                        self.cdelt[keep].copy(), [self.cunit[i] for i in keep])
 
 
+def _zenithal_pix2world(crpix, crval, psm, lonpole, proj, px, py, origin=0):
+    """(lon, lat) in degrees of pixel positions for a zenithal TAN / SIN projection (FITS WCS paper II, sections 2, 5.1):
+    pixel -> intermediate world coordinates -> native spherical (phi, theta) -> celestial, via unit vectors.  Host-side
+    and meant for a handful of points (image corners); the per-pixel map runs on the device (`sc_wcs_pixel_map`)."""
+    if proj not in ('TAN', 'SIN'):
+        raise NotImplementedError("celestial projection %r: TAN and SIN are implemented" % proj)
+    d2r = np.pi / 180.0
+    dx = np.asarray(px, dtype=np.float64) + (1 - origin) - crpix[0]
+    dy = np.asarray(py, dtype=np.float64) + (1 - origin) - crpix[1]
+    x = (psm[0, 0] * dx + psm[0, 1] * dy) * d2r
+    y = (psm[1, 0] * dx + psm[1, 1] * dy) * d2r
+    rr = x * x + y * y
+    if proj == 'TAN':                               # R_theta = cot(theta)
+        sin_t = 1.0 / np.sqrt(1.0 + rr)
+        n = np.stack([x * sin_t, -y * sin_t, sin_t])            # (cos t sin p, cos t cos p, sin t) in the native frame
+    else:                                           # R_theta = cos(theta)
+        with np.errstate(invalid='ignore'):
+            n = np.stack([x, -y, np.sqrt(1.0 - rr)])
+    # native -> celestial: the native pole (theta = 90 deg) sits at CRVAL, the celestial pole at native longitude LONPOLE
+    pp, dp = lonpole * d2r, crval[1] * d2r
+    a = n[1] * np.cos(pp) + n[0] * np.sin(pp)       # cos t cos(p - pp)
+    b = n[0] * np.cos(pp) - n[1] * np.sin(pp)       # cos t sin(p - pp)
+    zc = n[2] * np.sin(dp) + a * np.cos(dp)
+    xc = n[2] * np.cos(dp) - a * np.sin(dp)
+    lon = crval[0] + np.degrees(np.arctan2(-b, xc))
+    lat = np.degrees(np.arctan2(zc, np.hypot(xc, b)))
+    return lon, lat
+
+
+def _zenithal_world2pix(crpix, crval, psm, lonpole, proj, lon, lat, origin=0):
+    """Inverse of `_zenithal_pix2world`; positions behind the projection's horizon come back as NaN."""
+    if proj not in ('TAN', 'SIN'):
+        raise NotImplementedError("celestial projection %r: TAN and SIN are implemented" % proj)
+    d2r = np.pi / 180.0
+    da = (np.asarray(lon, dtype=np.float64) - crval[0]) * d2r
+    d, dp, pp = np.asarray(lat, dtype=np.float64) * d2r, crval[1] * d2r, lonpole * d2r
+    sin_t = np.sin(d) * np.sin(dp) + np.cos(d) * np.cos(dp) * np.cos(da)
+    a = np.sin(d) * np.cos(dp) - np.cos(d) * np.sin(dp) * np.cos(da)       # cos t cos(p - pp)
+    b = -np.cos(d) * np.sin(da)                                               # cos t sin(p - pp)
+    nx_ = b * np.cos(pp) + a * np.sin(pp)           # cos t sin p
+    ny_ = a * np.cos(pp) - b * np.sin(pp)           # cos t cos p
+    with np.errstate(divide='ignore', invalid='ignore'):
+        if proj == 'TAN':
+            x, y = np.where(sin_t > 0, nx_ / sin_t, np.nan), np.where(sin_t > 0, -ny_ / sin_t, np.nan)
+        else:
+            x, y = np.where(sin_t >= 0, nx_, np.nan), np.where(sin_t >= 0, -ny_, np.nan)
+    inv = np.linalg.inv(np.asarray(psm, dtype=np.float64)[:2, :2])
+    xd, yd = np.degrees(x), np.degrees(y)
+    return (inv[0, 0] * xd + inv[0, 1] * yd + crpix[0] - (1 - origin),
+            inv[1, 0] * xd + inv[1, 1] * yd + crpix[1] - (1 - origin))
+
+
 class CelestialWCS(object):
     def __init__(self, ctype, crval, crpix, cdelt, pc, lonpole):
         self.ctype, self.crval, self.crpix, self.cdelt, self.pc, self.lonpole = ctype, crval, crpix, cdelt, pc, lonpole
         self.naxis = 2
+
+    @property
+    def pixel_scale_matrix(self):
+        return np.asarray(self.cdelt, dtype=np.float64)[:, None] * np.asarray(self.pc, dtype=np.float64)
+
+    def pix2world(self, px, py, origin=0):
+        return _zenithal_pix2world(self.crpix, self.crval, self.pixel_scale_matrix, self.lonpole, self.ctype[0][-3:], px, py, origin)
+
+    def world2pix(self, lon, lat, origin=0):
+        return _zenithal_world2pix(self.crpix, self.crval, self.pixel_scale_matrix, self.lonpole, self.ctype[0][-3:], lon, lat, origin)
 
     def to_header(self):
         hdr = {}
