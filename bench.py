@@ -741,8 +741,9 @@ def section_c5(job, line):
             ms_r = job.timeit(lambda: cc.reproject(hdr), n=3, warm=1)
             Vr = nloc * ny * nx
             out['reproject'] = {'ms': ms_r, 'planes_per_gpu': nloc, 'voxels_per_s': Vr * world / (ms_r * 1e-3),
-                                'roofline': job.roof(4 * Vr + 13 * Vr + 16 * ny * nx, ms_r,
-                                                     'wcs_pixel_map_kernel + reproject_tiled_kernel (f64 + f32 + footprint out)',
+                                'roofline': job.roof(4 * Vr + 9 * Vr + 16 * ny * nx, ms_r,
+                                                     'wcs_pixel_map_kernel + reproject_tiled_kernel (f64 + footprint out; the float32 '
+                                                     'working copy is made lazily)',
                                                      parity='oracle unpinned (oracle/reproject.py)')}
             del planes, cc
     line['c5'] = out

@@ -125,7 +125,10 @@ class BaseSpectralCube(object):
     def __init__(self, data, wcs, mask=None, meta=None, fill_value=np.nan, header=None,
                  allow_huge_operations=False, unit=None, spectral_unit=None, device=None, **kwargs):
         torch = _torch()
-        if isinstance(data, torch.Tensor):
+        deferred = data if isinstance(data, _PendingFloat32Copy) else None
+        if deferred is not None:
+            t = deferred.hi                          # (only its shape is looked at below)
+        elif isinstance(data, torch.Tensor):
             t = data
             if t.dtype != torch.float32:
                 t = t.to(torch.float32)
@@ -145,10 +148,10 @@ class BaseSpectralCube(object):
         sc = t.stride(0) if t.shape[0] > 1 and t.stride(0) >= t.shape[1] * sy else t.shape[1] * sy
         if (t.shape[1] == 1 and t.stride(1) != sy) or (t.shape[0] == 1 and t.stride(0) != sc):
             t = t.as_strided(tuple(t.shape), (sc, sy, 1), t.storage_offset())
-        self._data_t = t
-        self._hi = None                 # float64 tensor when the numpy-class semantics produce one ...
+        self._data_t = t if deferred is None else None
+        self._hi = None if deferred is None else deferred.hi    # float64 tensor when the numpy-class semantics produce one ...
         self._hi_is_widened_f32 = False # ... or a flag: the float64 the reference returns is the float32 copy widened
-        self._pending = None            # lazy op recorded by DaskSpectralCube (see spectral_smooth)
+        self._pending = deferred        # lazy op recorded by DaskSpectralCube (see spectral_smooth) / float32 copy not made yet
         self._wcs = as_cube_wcs(wcs)
         if mask is not None and not isinstance(mask, MaskBase):
             mask = BooleanArrayMask(np.asarray(mask, dtype=bool), self._wcs, shape=tuple(t.shape))
@@ -196,7 +199,7 @@ class BaseSpectralCube(object):
         """spectral_cube.py:244-289"""
         cls = cls or type(self)
         cube = cls.__new__(cls)
-        still_lazy = data is None and self._data_t is None
+        still_lazy = data is None and self._data_t is None and isinstance(self._pending, _PendingSpectralSmooth)
         if still_lazy:
             data = self._pending.source._data            # placeholder; replaced below
         BaseSpectralCube.__init__(
@@ -383,7 +386,12 @@ class BaseSpectralCube(object):
             torch = _torch()
             if self._mask is None:
                 return self._data_hi.cpu().numpy()[view]
-            inc = self._mask._include_tensor(self._data).bool()
+            if isinstance(self._mask, BooleanArrayMask) and self._data_t is None:
+                # a freshly reprojected cube: the mask is the footprint array itself, no need for the float32 copy
+                inc = self._mask._mask.bool() if self._mask._mask_type == 'include' else ~self._mask._mask.bool()
+                inc = inc.expand(self.shape) if tuple(inc.shape) != tuple(self.shape) else inc
+            else:
+                inc = self._mask._include_tensor(self._data).bool()
             return torch.where(inc, self._data_hi, torch.full((), float(fill), dtype=torch.float64,
                                                               device=self._data_hi.device)).cpu().numpy()[view]
         return self._filled_tensor(fill).cpu().numpy()[view]
@@ -794,7 +802,7 @@ class BaseSpectralCube(object):
         _lib.check(lib.sc_wcs_pixel_map(op, ip, ny_out, nx_out, yin.data_ptr(), xin.data_ptr(), _stream()))
         return yin, xin
 
-    def _run_reproject(self, yin, xin, order, filled=True, out_dtype=None):
+    def _run_reproject(self, yin, xin, order, filled=True, out_dtype=None, want_f32=False):
         """One pass: the float64 result `reproject_interp` returns, its float32 working copy, the
         footprint and the "anything valid at all" flag (spectral_cube.py:2726-2746)."""
         torch = _torch()
@@ -805,7 +813,8 @@ class BaseSpectralCube(object):
         out_dtype = _lib.F64 if out_dtype is None else out_dtype
         out = torch.empty((nchan, ny_out, nx_out), dtype=torch.float64 if out_dtype == _lib.F64 else torch.float32,
                           device=src.device)
-        out32 = torch.empty((nchan, ny_out, nx_out), dtype=torch.float32, device=src.device) if out_dtype == _lib.F64 else None
+        out32 = (torch.empty((nchan, ny_out, nx_out), dtype=torch.float32, device=src.device)
+                 if out_dtype == _lib.F64 and want_f32 else None)
         foot = torch.empty((nchan, ny_out, nx_out), dtype=torch.uint8, device=src.device)
         flag = torch.empty((1,), dtype=torch.int32, device=src.device)
         desc, keep = self._mask_desc() if filled else lower_mask(None, src)
@@ -813,7 +822,7 @@ class BaseSpectralCube(object):
                                        out32.data_ptr() if out32 is not None else None, foot.data_ptr(), flag.data_ptr(),
                                        nchan, ny, nx, src.stride(0), src.stride(1), ny_out, nx_out, desc,
                                        float(self._fill_value), yin.data_ptr(), xin.data_ptr(), order, _stream()))
-        return out, (out32 if out32 is not None else out), foot, flag
+        return out, (out32 if out32 is not None else (out if out_dtype != _lib.F64 else None)), foot, flag
 
     def reproject(self, header, order='bilinear', use_memmap=False, filled=True, **kwargs):
         """Spatially reproject the cube into a new header (a FITS-header-like mapping with NAXISn and
@@ -840,8 +849,8 @@ class BaseSpectralCube(object):
                              "whether the WCS transformation produces valid pixel->world "
                              "and world->pixel coordinates in each axis.")
         newmask = BooleanArrayMask(foot, wcs=newwcs)
-        cube = self._new_cube_with(data=out32, wcs=newwcs, mask=newmask)
-        cube._data_hi = out                        # reproject_interp returns float64
+        # reproject_interp returns float64: that is the cube's data; its float32 working copy is made on first use
+        cube = self._new_cube_with(data=_PendingFloat32Copy(out), wcs=newwcs, mask=newmask)
         cube._mask = newmask
         return cube
 
@@ -1090,6 +1099,33 @@ class BaseSpectralCube(object):
     def linewidth_fwhm(self, how='auto', **kwargs):
         s = self.linewidth_sigma(**kwargs)               # the reference drops `how` here (:1763)
         return s._with(s.value * SIGMA2FWHM, s.unit)
+
+
+class _PendingFloat32Copy(object):
+    """The float32 working copy of a cube whose result is float64 (`reproject` returns what `reproject_interp` does),
+    not made until something asks for it: `_data_hi`, `unmasked_data`, `filled_data`, `write` and `mosaic_cubes` read
+    the float64 tensor, and the reproject kernel saves 4 of its 13 output bytes per voxel."""
+
+    def __init__(self, hi):
+        self.hi = hi
+        self.shape = tuple(hi.shape)
+        self.source = self                 # `.source._data.device` is where the cube lives
+
+    @property
+    def _data(self):
+        return self.hi
+
+    @property
+    def _data_t(self):
+        return self.hi
+
+    def materialize(self):
+        return self.hi.to(_torch().float32)
+
+    def moments(self, cube, want_bits):
+        cube._data                          # makes the float32 copy; the cube is an ordinary one from here on
+        cube._pending = None
+        return cube._moments_axis0_raw(want_bits)
 
 
 class _PendingSpectralSmooth(object):
