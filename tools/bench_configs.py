@@ -50,7 +50,7 @@ def emit(config, what, voxels, ms, algo_bytes, **extra):
 
 
 def isfinite_cube(cls, dev, w):
-    c = cls(dev, w, unit='K')
+    c = cls(dev, w, unit='K', allow_huge_operations=True)
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     return c
 
