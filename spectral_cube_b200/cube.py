@@ -374,6 +374,10 @@ class BaseSpectralCube(object):
         lib = _lib.load()
         if self._mask is None:
             return self._data
+        if getattr(self, '_nan_filled_already', False) and fill != fill:
+            # the data of a freshly interpolated cube are NaN wherever its new mask excludes them (both bracketing samples
+            # were masked: spectral_cube.py:3305-3313, dask :1364): filling with NaN changes nothing, no pass needed
+            return self._data
         desc, keep = self._mask_desc()
         out = torch.empty(self.shape, dtype=torch.float32, device=self._data.device)
         nchan, ny, nx = self.shape
@@ -786,6 +790,7 @@ class BaseSpectralCube(object):
         else:
             cube = self._new_cube_with(data=out, wcs=newwcs, mask=newmask)
         cube._mask = newmask
+        cube._nan_filled_already = (fill_value is None or fill_value != fill_value) and (dask or float(self._fill_value) != float(self._fill_value))
         return cube
 
     # -- reprojection (spectral_cube.py:2649-2746) -------------------------------------------------------
