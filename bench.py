@@ -723,10 +723,22 @@ def section_c5(job, line):
             del dev, c
             job.free()
             sh = D.RowShardedCube(interp, ny, y0, None)
-            ms_x = job.timeit(lambda: D.reshard_rows_to_channels(interp._data, ny), n=3, warm=1)
-            out['reshard_all_to_all'] = {'ms': ms_x, 'bytes_sent_per_gpu': int(interp._data.numel() * 4 * (world - 1) // world)}
-            ms_r = job.timeit(lambda: sh.reproject(hdr), n=2, warm=1)
-            out['reproject_sharded'] = {'ms': ms_r, 'what': 'fill + rows->channels all-to-all + pixel map + bilinear'}
+            sent = int(interp._data.numel() * 4 * (world - 1) // world)
+            ms_x = job.timeit(lambda: D.reshard_rows_to_channels(interp._data, ny, mode='nccl'), n=3, warm=1)
+            out['reshard_all_to_all'] = {'ms': ms_x, 'bytes_sent_per_gpu': sent, 'GBps_per_gpu_per_direction': sent / ms_x / 1e6,
+                                         'what': 'NCCL all_to_all into per-source blocks + concatenation'}
+            mode = 'nccl'
+            try:
+                ms_p = job.timeit(lambda: D.reshard_rows_to_channels(interp._data, ny, mode='peer', borrow=True), n=3, warm=1)
+                out['reshard_peer'] = {'ms': ms_p, 'bytes_sent_per_gpu': sent, 'GBps_per_gpu_per_direction': sent / ms_p / 1e6,
+                                       'what': 'sc_reshard_scatter: one kernel per rank storing into the destination ranks\' final '
+                                               'layout over NVLink peer memory (symmetric buffers), barriers included',
+                                       'nvlink_peak_GBps_per_direction': 770.0}
+                mode = 'peer'
+            except Exception as exc:
+                out['reshard_peer'] = {'unavailable': repr(exc)[:300]}
+            ms_r = job.timeit(lambda: sh.reproject(hdr, reshard_mode=mode), n=2, warm=1)
+            out['reproject_sharded'] = {'ms': ms_r, 'reshard': mode, 'what': 'rows->channels re-shard + pixel map + bilinear'}
             out['ms'] = ms_i + ms_r
             out['value'] = V / ((ms_i + ms_r) * 1e-3)
             out['unit'] = 'voxels/s'

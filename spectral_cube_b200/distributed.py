@@ -79,8 +79,60 @@ def exchange_halo_rows(top_edge, bot_edge, group=None, mode='p2p'):
     return halo_top, halo_bot
 
 
-def reshard_rows_to_channels(local, ny_total, group=None):
-    """(nchan, rows_r, nx) row shard -> (chans_r, ny_total, nx) channel shard with one all-to-all."""
+_PEER = {'buffers': {}, 'broken': None}
+
+
+def _peer_buffer(shape, device, group):
+    """A symmetric (same shape on every rank) float32 buffer with every peer's copy mapped into this process:
+    (tensor, handle).  Cached per shape: the allocation and the rendezvous (an exchange of memory handles) happen once."""
+    import torch
+    import torch.distributed._symmetric_memory as symm
+    dist = _dist()
+    key = (tuple(shape), str(device), id(group))
+    if key not in _PEER['buffers']:
+        t = symm.empty(*shape, dtype=torch.float32, device=device)
+        hdl = symm.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+        _PEER['buffers'][key] = (t, hdl)
+    return _PEER['buffers'][key]
+
+
+def release_peer_buffers():
+    _PEER['buffers'].clear()
+
+
+def _reshard_rows_to_channels_peer(local, ny_total, group, borrow):
+    """One kernel per rank stores every channel of the local row block straight into its final place in the
+    destination rank's buffer over NVLink peer memory (`sc_reshard_scatter`): no staging, no concatenation pass."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    dist = _dist()
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nchan, rows, nx = local.shape
+    cparts = channel_partition(nchan, world)
+    y0 = row_partition(ny_total, world)[rank][0]
+    chans_max = max(c1 - c0 for c0, c1 in cparts)
+    buf, hdl = _peer_buffer((chans_max, ny_total, nx), local.device, group)
+    ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+    bounds = (C.c_int64 * (world + 1))(*([c0 for c0, _ in cparts] + [nchan]))
+    with _lib.on_device_of(local):
+        stream = torch.cuda.current_stream().cuda_stream
+        hdl.barrier()                                     # every rank is done reading the buffer's previous contents
+        _lib.check(lib.sc_reshard_scatter(local.data_ptr(), nchan, rows, nx, local.stride(0), local.stride(1),
+                                          ptrs, world, bounds, ny_total, y0, stream))
+        hdl.barrier()                                     # every rank's stores have landed
+    mine = buf[:cparts[rank][1] - cparts[rank][0]]
+    return mine if borrow else mine.clone()
+
+
+def reshard_rows_to_channels(local, ny_total, group=None, mode='auto', borrow=False):
+    """(nchan, rows_r, nx) row shard -> (chans_r, ny_total, nx) channel shard.
+
+    ``mode='peer'``: one scatter kernel per rank over NVLink peer memory (needs CUDA tensors, float32, nx % 4 == 0 and
+    torch's symmetric memory); ``mode='nccl'``: one NCCL all-to-all into per-source blocks plus a concatenation pass;
+    ``'auto'`` takes the peer path when it is available.  ``borrow=True`` returns a view of the (reused) peer buffer,
+    valid until the next re-shard of the same shape."""
     import torch
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -89,6 +141,21 @@ def reshard_rows_to_channels(local, ny_total, group=None):
     rparts = row_partition(ny_total, world)
     if world == 1:
         return local
+    if mode not in ('auto', 'peer', 'nccl'):
+        raise ValueError("mode must be 'auto', 'peer' or 'nccl'")
+    peer_ok = (local.is_cuda and local.dtype == torch.float32 and nx % 4 == 0 and local.stride(2) == 1 and
+               local.stride(0) % 4 == 0 and local.stride(1) % 4 == 0 and world <= 16 and dist.get_backend(group) == 'nccl')
+    if mode == 'peer' and not peer_ok:
+        raise ValueError("the peer re-shard needs CUDA float32 rows of a multiple of 4 samples under an NCCL group of <= 16 ranks")
+    if mode != 'nccl' and peer_ok and _PEER['broken'] is None:
+        try:
+            return _reshard_rows_to_channels_peer(local, ny_total, group, borrow)
+        except Exception as exc:                           # no symmetric memory on this platform: say so once, use NCCL
+            if mode == 'peer':
+                raise
+            import warnings
+            _PEER['broken'] = repr(exc)
+            warnings.warn("peer-memory re-shard unavailable (%s); using the NCCL all-to-all" % (_PEER['broken'][:200],))
     send = [local[c0:c1].contiguous() for (c0, c1) in cparts]
     my_c0, my_c1 = cparts[rank]
     recv = [torch.empty((my_c1 - my_c0, y1 - y0, nx), dtype=local.dtype, device=local.device) for (y0, y1) in rparts]
@@ -323,7 +390,8 @@ class RowShardedCube(object):
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         loc = self.local
         filled_rows = loc._filled_tensor(loc._fill_value) if filled else loc._data
-        chan_local = reshard_rows_to_channels(filled_rows, self.ny_total, self.group)
+        chan_local = reshard_rows_to_channels(filled_rows, self.ny_total, self.group, mode=kw.pop('reshard_mode', 'auto'),
+                                              borrow=True)     # consumed by the reproject call below
         c0, c1 = channel_partition(loc.shape[0], world)[rank]
         w = loc._wcs.copy()
         w.crpix[1] += self.y0                                  # back to the full image's WCS

@@ -68,6 +68,15 @@ def sharded_parity(group=None, rows_per_rank=48):
             ref = w2.convolve_to(Beam(5 * pix))._data
             got = s2.convolve_to(Beam(5 * pix)).local._data
             res['convolve_to_' + cls.__name__] = same(got, ref[:, y0:y1], 'convolve_to_' + cls.__name__)
+        # the rows -> channels re-shard: NCCL all-to-all against the peer-memory scatter kernel (when the platform has it)
+        via_nccl = D.reshard_rows_to_channels(local, ny, mode='nccl')
+        c0, c1 = D.channel_partition(nchan, world)[rank]
+        res['reshard_nccl'] = same(via_nccl, full[c0:c1], 'reshard_nccl')
+        try:
+            via_peer = D.reshard_rows_to_channels(local, ny, mode='peer')
+            res['reshard_peer'] = same(via_peer, full[c0:c1], 'reshard_peer')
+        except Exception as exc:                      # reported, not a parity failure: the NCCL path serves
+            detail['reshard_peer_unavailable'] = repr(exc)[:300]
         a = np.radians(30.0)
         hdr = dict(whole.header)
         hdr.update({'PC1_1': np.cos(a), 'PC1_2': -np.sin(a), 'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
