@@ -276,11 +276,12 @@ int sc_scale(void *data, int dtype, int64_t nchan, int64_t ny, int64_t nx,
  * one host): this rank's block `local` (nchan, rows, nx) -- rows [y0, y0 + rows) of the image -- is stored channel by
  * channel into the destination ranks' (chan_bounds[d+1] - chan_bounds[d], ny_total, nx) buffers, `peer_ptrs[d]` being rank d's
  * buffer as mapped into THIS process (device pointers in a host array of `world` entries, e.g. the `buffer_ptrs` of a
- * torch symmetric-memory handle).  One kernel, one read of the local block, peer stores of 16-byte vectors; the caller
+ * torch symmetric-memory handle).  One kernel, one read of the local block, peer stores of 16-byte vectors, destinations
+ * interleaved line by line starting at `rank`'s neighbour so that no peer's ingress is a hot spot; the caller
  * orders it against the other ranks (barrier before: the buffers are free; barrier after: all stores have landed). */
 int sc_reshard_scatter(const float *local, int64_t nchan, int64_t rows, int64_t nx,
                        int64_t stride_c, int64_t stride_y,
-                       const uint64_t *peer_ptrs, int world, const int64_t *chan_bounds,
+                       const uint64_t *peer_ptrs, int world, int rank, const int64_t *chan_bounds,
                        int64_t ny_total, int64_t y0, void *stream);
 
 int sc_mosaic_accumulate(double *acc, double *weight, const void *reprojected, int dtype, const uint8_t *footprint0,

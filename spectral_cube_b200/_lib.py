@@ -89,7 +89,7 @@ SIGNATURES = {
     'sc_spatial_smooth_2d': (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
                                     _pd, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     'sc_scale': (_i32, [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _dbl, _i32, _vp, _vp]),
-    'sc_reshard_scatter': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(C.c_uint64), _i32, C.POINTER(C.c_int64),
+    'sc_reshard_scatter': (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(C.c_uint64), _i32, _i32, C.POINTER(C.c_int64),
                                   _i64, _i64, _vp]),
     'sc_mosaic_accumulate': (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _vp]),
     'sc_mosaic_normalize': (_i32, [_vp, _vp, _i64, _i64, _i64, _vp]),

@@ -120,7 +120,7 @@ def _reshard_rows_to_channels_peer(local, ny_total, group, borrow):
         stream = torch.cuda.current_stream().cuda_stream
         hdl.barrier()                                     # every rank is done reading the buffer's previous contents
         _lib.check(lib.sc_reshard_scatter(local.data_ptr(), nchan, rows, nx, local.stride(0), local.stride(1),
-                                          ptrs, world, bounds, ny_total, y0, stream))
+                                          ptrs, world, rank, bounds, ny_total, y0, stream))
         hdl.barrier()                                     # every rank's stores have landed
     mine = buf[:cparts[rank][1] - cparts[rank][0]]
     return mine if borrow else mine.clone()
