@@ -702,8 +702,7 @@ constexpr int PP_WD = SP_W + 2;            // padded widened row (doubles): the 
 constexpr int PP_TOP = SP_TX + 2;          // padded ring row (doubles)
 constexpr int PP_CAP = 64;                 // listed missing inputs per block; more -> dense integer row deficits
 constexpr int PP_FULL = PP_R * SP_W;       // every sample of the block's window missing
-constexpr int PP_GROUP = 128;              // threads per role
-constexpr int PP_THREADS = 2 * PP_GROUP + 32;
+constexpr int PP_DEFAULT_J = 8;            // outputs per thread in both passes (see sep_pipe_kernel): 8.4 ms against 9.3-10.6 ms with 16
 enum { PM_CLEAN = 0, PM_SPARSE = 1, PM_CROWDED = 2, PM_BLANK = 3 };
 
 struct PipeSmem {
@@ -723,8 +722,9 @@ struct PipeSmem {
 static_assert(offsetof(PipeSmem, wd) % 16 == 0 && offsetof(PipeSmem, rowdef) % 16 == 0 && offsetof(PipeSmem, raw) % 16 == 0 &&
               offsetof(PipeSmem, qyp) % 16 == 0, "vector accesses need 16-byte aligned members");
 
-__device__ __forceinline__ void pipe_bar(int id) {          // barrier among the 128 row threads
-    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(PP_GROUP) : "memory");
+template <int NTHR>
+__device__ __forceinline__ void pipe_bar(int id) {          // barrier among the row threads
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NTHR) : "memory");
 }
 
 // a register copy of a kernel parameter that the compiler cannot fold back into a constant-bank operand
@@ -758,15 +758,16 @@ __device__ __forceinline__ double place_scaled_finite(float v) {
     return __hiloint2double((b >> 3) & 0x8FFFFFFF, b << 29);
 }
 
-// (1, fast) widen an interior block: 16 rows x 80 pairs, warp w takes rows 4w .. 4w+3; returns the missing-element bits
-template <bool FINITE>
+// (1, fast) widen an interior block: 16 rows x 80 pairs, warp w takes rows RW w .. RW w + RW - 1 (RW = 4 with four row
+// warps, 2 with eight); returns the missing-element bits (bit 2i + e: element e of this thread's pair i)
+template <bool FINITE, int RW>
 __device__ __forceinline__ uint32_t pipe_widen_fast(PipeSmem &sm, int s, int par, int warp, int lane, float lo_c, float hi_c) {
     uint32_t miss = 0u;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        // passes 0..7: row 4w + i/2, pairs 32 (i&1) + lane; passes 8, 9: the last 16 pairs of rows 4w + 2(i-8) + (lane>>4)
-        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
-        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+    for (int i = 0; i < RW * 5 / 2; ++i) {
+        // passes 0 .. 2RW-1: row RW w + i/2, pairs 32 (i&1) + lane; the RW/2 passes after them: the last 16 pairs of two rows each
+        const int row = i < 2 * RW ? RW * warp + (i >> 1) : RW * warp + 2 * (i - 2 * RW) + (lane >> 4);
+        const int pc = i < 2 * RW ? 32 * (i & 1) + lane : 64 + (lane & 15);
         const float2 v = *reinterpret_cast<const float2 *>(&sm.raw[s][row][2 * pc]);
         const bool ok0 = (v.x >= lo_c) & (v.x <= hi_c);           // false for NaN
         const bool ok1 = (v.y >= lo_c) & (v.y <= hi_c);
@@ -778,13 +779,18 @@ __device__ __forceinline__ uint32_t pipe_widen_fast(PipeSmem &sm, int s, int par
     return miss;
 }
 
+__device__ __forceinline__ void pipe_pair_of(int i, int rw, int warp, int lane, int &row, int &pc) {
+    row = i < 2 * rw ? rw * warp + (i >> 1) : rw * warp + 2 * (i - 2 * rw) + (lane >> 4);
+    pc = i < 2 * rw ? 32 * (i & 1) + lane : 64 + (lane & 15);
+}
+
 // (1, slow) widen a block that touches the image border, halo rows or a mask the interval test cannot express
-__device__ __noinline__ void pipe_widen_slow(const SpatialParams &p, PipeSmem &sm, int s, int par, int l3, int warp, int lane,
+__device__ __noinline__ void pipe_widen_slow(const SpatialParams &p, PipeSmem &sm, int s, int par, int l3, int rw, int warp, int lane,
                                              const PipeBlock &k) {
 #pragma unroll 1
-    for (int i = 0; i < 10; ++i) {
-        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
-        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+    for (int i = 0; i < rw * 5 / 2; ++i) {
+        int row, pc;
+        pipe_pair_of(i, rw, warp, lane, row, pc);
         const float vx = pipe_filled(p, sm.raw[s], row, 2 * pc, k);
         const float vy = pipe_filled(p, sm.raw[s], row, 2 * pc + 1, k);
         const bool ok0 = vx == vx, ok1 = vy == vy;
@@ -794,15 +800,15 @@ __device__ __noinline__ void pipe_widen_slow(const SpatialParams &p, PipeSmem &s
     }
 }
 
-// (4) crowded block (more than PP_CAP missing inputs: blank frames, masked regions): the row deficits of one thread's 16
+// (4) crowded block (more than PP_CAP missing inputs: blank frames, masked regions): the row deficits of one thread's J
 // outputs from the RUNS of missing inputs in its window -- a run [i0, i1] adds qx[j + 2H - i1] + .. + qx[j + 2H - i0] to output j,
 // two look-ups in the clamped prefix-sum table whatever its length.  Step A (all row threads, then a barrier): per-row missing
-// bits by warp ballot; step B: this thread's 16 + 2H window bits, run by run.
-__device__ __noinline__ void pipe_crowded_masks(const SpatialParams &p, PipeSmem &sm, int s, int warp, int lane,
+// bits by warp ballot; step B: this thread's J + 2H window bits, run by run.
+__device__ __noinline__ void pipe_crowded_masks(const SpatialParams &p, PipeSmem &sm, int s, int rw, int warp, int lane,
                                                 bool slow, float lo_c, float hi_c, const PipeBlock &k) {
 #pragma unroll 1
-    for (int rr = 0; rr < 4; ++rr) {
-        const int row = 4 * warp + rr;
+    for (int rr = 0; rr < rw; ++rr) {
+        const int row = rw * warp + rr;
 #pragma unroll 1
         for (int q = 0; q < SP_W / 32; ++q) {
             const int col = 32 * q + lane;
@@ -814,12 +820,13 @@ __device__ __noinline__ void pipe_crowded_masks(const SpatialParams &p, PipeSmem
     }
 }
 
+template <int J>
 __device__ __noinline__ void pipe_crowded_rowdef(PipeSmem &sm, int slot, int rrow, int seg, int h) {
-    uint32_t dx[16];
+    uint32_t dx[J];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dx[j] = 0u;
-    const int nin = PP_R + 2 * h;
-    const int w0 = seg * 16 + SP_HP - h;                          // first window column
+    for (int j = 0; j < J; ++j) dx[j] = 0u;
+    const int nin = J + 2 * h;
+    const int w0 = seg * J + SP_HP - h;                           // first window column
     const uint32_t *m = &sm.rowmask[rrow][w0 >> 5];
     const int sh = w0 & 31;
     const uint32_t lo = __funnelshift_r(m[0], m[1], sh), hi = __funnelshift_r(m[1], m[2], sh);
@@ -834,20 +841,27 @@ __device__ __noinline__ void pipe_crowded_rowdef(PipeSmem &sm, int slot, int rro
         // sum over i in [i0, i1] of qx[j + 2h - i] = cqx[j + 2h - i0 + 1] - cqx[j + 2h - i1], indices clamped to [0, nt]
         const uint32_t *hi_t = &sm.cqxp[64 + 2 * h - i0 + 1], *lo_t = &sm.cqxp[64 + 2 * h - i1];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dx[j] += hi_t[j] - lo_t[j];
+        for (int j = 0; j < J; ++j) dx[j] += hi_t[j] - lo_t[j];
     }
 #pragma unroll
-    for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + rrow][seg * 16 + j]) = make_uint4(dx[j], dx[j + 1], dx[j + 2], dx[j + 3]);
+    for (int j = 0; j < J; j += 4)
+        *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + rrow][seg * J + j]) = make_uint4(dx[j], dx[j + 1], dx[j + 2], dx[j + 3]);
 }
 
-template <int H, int OUT64>
-__global__ void __launch_bounds__(PP_THREADS, 1)
+// J = outputs per thread in both passes: 16 -> 4 row warps + 4 column warps (fewest shared-memory loads per output),
+// 8 -> 8 + 8 (two warps per role and scheduler: more latency hiding, 1.6x the shared-memory traffic of the passes)
+template <int H, int OUT64, int J>
+__global__ void __launch_bounds__(2 * (PP_R * SP_TX / J) + 32, 1)
 sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
     if (p.sel && sel_wants_march(p.sel)) return;         // too many missing samples: the convolved denominator is cheaper
     constexpr int NT = 2 * H + 1;
-    constexpr int NIN = PP_R + 2 * H;                    // inputs of 16 outputs
+    constexpr int NIN = J + 2 * H;                       // inputs of J outputs
+    constexpr int GROUP = PP_R * SP_TX / J;              // threads per role
+    constexpr int NWARP = GROUP / 32;                    // warps per role
+    constexpr int RW = PP_R / NWARP;                     // rows a row warp widens
+    constexpr int NTHREADS = 2 * GROUP + 32;
     static_assert(H <= SP_HP && H <= PP_R && (H % 2) == 0, "half-width");
+    static_assert(J == 8 || J == 16, "outputs per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem &sm = *reinterpret_cast<PipeSmem *>(smem_raw);
 
@@ -869,23 +883,24 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
     const uint32_t row_bytes = (uint32_t)(xr - xl) * 4u;
 
     if (tid == 0) {
-        for (int s = 0; s < PP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PP_GROUP / 32); }
-        for (int q = 0; q < PP_NB; ++q) { mbar_init(&sm.rfull[q], PP_GROUP / 32); mbar_init(&sm.rempty[q], PP_GROUP / 32); }
+        for (int s = 0; s < PP_RS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NWARP); }
+        for (int q = 0; q < PP_NB; ++q) { mbar_init(&sm.rfull[q], NWARP); mbar_init(&sm.rempty[q], NWARP); }
         mbar_fence_init();
         sm.count[0] = sm.count[1] = sm.count[2] = 0;
     }
     if (tid < 96) { const int k = tid - 32; sm.qyp[tid] = (k >= 0 && k < NT) ? p.qy[k] : 0u; }
     if (tid >= 96 && tid < 256) { const int t = tid - 96, k = t - 64; sm.cqxp[t] = p.cqx[k < 0 ? 0 : (k > NT ? NT : k)]; }
+
     // the columns of the raw rows that lie outside the image are never written by the copies: valid zeros, set once
     if (col_off > 0 || (int)(xr - xl) < SP_W) {
-        for (int i = tid; i < PP_RS * PP_R * SP_W; i += PP_THREADS) {
+        for (int i = tid; i < PP_RS * PP_R * SP_W; i += NTHREADS) {
             const int col = i % SP_W;
             if (col < col_off || col >= col_off + (int)(xr - xl)) (&sm.raw[0][0][0])[i] = 0.0f;
         }
     }
     __syncthreads();
 
-    if (warp == 2 * PP_GROUP / 32) {
+    if (warp == 2 * NWARP) {
         // ---------------- producer warp ----------------
         const uint64_t pol = l2_evict_first_policy();
         for (int b = 0; b < nblk; ++b) {
@@ -921,10 +936,10 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
     // zero padding is a VALID sample: the fast path's interval test may run over it only if the interval contains 0
     const bool zero_ok = p.mask.mode != MODE_INTERVAL || (p.lo_closed <= 0.0f && p.hi_closed >= 0.0f);
 
-    if (warp < PP_GROUP / 32) {
+    if (warp < NWARP) {
         // ================= row warps =================
-        const int t = tid;                               // 0 .. 127
-        const int rrow = t & 15, seg = t >> 4;
+        const int t = tid;                               // 0 .. GROUP - 1
+        const int rrow = t & 15, seg = t >> 4;           // row of the block, segment of J columns
         double T[NT];
 #pragma unroll
         for (int k = 0; k < NT; ++k) T[k] = reg_copy(p.tx_scaled[k]);
@@ -940,16 +955,16 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
             if (t == 0) sm.count[(b + 1) % 3] = 0;       // last read two blocks ago, next written after this block's barrier
             mbar_wait(&sm.full[s], (b / PP_RS) & 1);
 
-            // ---- (1) widen every input once: 16 rows x 80 pairs; warp w takes rows 4w .. 4w+3 ----
+            // ---- (1) widen every input once: 16 rows x 80 pairs ----
             if (slow) {
-                pipe_widen_slow(p, sm, s, par, l3, warp, lane, blk);
+                pipe_widen_slow(p, sm, s, par, l3, RW, warp, lane, blk);
             } else {
                 // bit 2i + e of `miss`: element e of this thread's pair i is missing (listed after the loop: the common
                 // iteration is branch-free).  Under an interval mask the bounds are finite, so +-inf is "missing" and the
                 // placement needs no special case for it.
                 uint32_t miss = 0u;
-                if (p.mask.mode == MODE_INTERVAL) miss = pipe_widen_fast<true>(sm, s, par, warp, lane, lo_c, hi_c);
-                else                              miss = pipe_widen_fast<false>(sm, s, par, warp, lane, lo_c, hi_c);
+                if (p.mask.mode == MODE_INTERVAL) miss = pipe_widen_fast<true, RW>(sm, s, par, warp, lane, lo_c, hi_c);
+                else                              miss = pipe_widen_fast<false, RW>(sm, s, par, warp, lane, lo_c, hi_c);
                 if (__ballot_sync(0xffffffffu, miss != 0u)) {           // warp-uniform: ONE atomic per warp whatever the count
                     const int n = __popc(miss);
                     int incl = n;
@@ -961,14 +976,13 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     while (miss && idx < PP_CAP) {
                         const int bit = __ffs((int)miss) - 1;
                         miss &= miss - 1u;
-                        const int i = bit >> 1;
-                        const int row = i < 8 ? 4 * warp + (i >> 1) : 4 * warp + 2 * (i - 8) + (lane >> 4);
-                        const int pc = i < 8 ? 32 * (i & 1) + lane : 64 + (lane & 15);
+                        int row, pc;
+                        pipe_pair_of(bit >> 1, RW, warp, lane, row, pc);
                         sm.list[l3][idx++] = (uint16_t)((row << 8) | (2 * pc + (bit & 1)));
                     }
                 }
             }
-            pipe_bar(1);
+            pipe_bar<GROUP>(1);
             const int cnt = sm.count[l3];                // uniform
             const int mode = cnt == 0 ? PM_CLEAN : cnt == PP_FULL ? PM_BLANK : cnt <= PP_CAP ? PM_SPARSE : PM_CROWDED;
             if (mode != PM_CROWDED) {                    // (a crowded block re-reads the raw rows for its dense deficits)
@@ -981,11 +995,12 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
 
             // ---- (2) sparse block: scatter the listed inputs' qx[.] into the (zeroed) row-deficit plane ----
             if (mode == PM_SPARSE) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + 4 * i + (t >> 5)][4 * (t & 31)]) = make_uint4(0u, 0u, 0u, 0u);
-                pipe_bar(2);
-                for (int e = warp; e < cnt; e += PP_GROUP / 32) {
+                // (clearing the plane here, by the row warps, beats clearing the dirty rows in the column warps when they
+                //  release a block: 8.4 against 8.7 ms -- the column warps are the critical path)
+                for (int i = t; i < PP_R * SP_TX / 4; i += GROUP)
+                    *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + (i >> 5)][4 * (i & 31)]) = make_uint4(0u, 0u, 0u, 0u);
+                pipe_bar<GROUP>(2);
+                for (int e = warp; e < cnt; e += NWARP) {
                     const int ent = sm.list[l3][e];
                     const int r_in = ent >> 8, cin = ent & 255;
                     const int xo0 = cin - SP_HP - H;                       // out(xo) reads in(xo + H - k): xo = xo0 + k
@@ -1000,16 +1015,16 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                 }
             }
 
-            // ---- (3) row pass: 16 adjacent outputs of row `rrow` from 16 + 2H widened inputs ----
-            double *trow = &sm.top[slot * PP_R + rrow][seg * 16];
+            // ---- (3) row pass: J adjacent outputs of row `rrow` from J + 2H widened inputs ----
+            double *trow = &sm.top[slot * PP_R + rrow][seg * J];
             if (mode == PM_BLANK) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(0.0, 0.0);
+                for (int j = 0; j < J; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(0.0, 0.0);
             } else {
-                const double2 *src = reinterpret_cast<const double2 *>(&sm.wd[par][rrow][seg * 16 + SP_HP - H]);
-                double acc[16];
+                const double2 *src = reinterpret_cast<const double2 *>(&sm.wd[par][rrow][seg * J + SP_HP - H]);
+                double acc[J];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+                for (int j = 0; j < J; ++j) acc[j] = 0.0;
 #pragma unroll
                 for (int q = 0; q < NIN / 2; ++q) {
                     const double2 v2 = src[q];
@@ -1018,22 +1033,22 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                         const double v = e ? v2.y : v2.x;
                         const int i = 2 * q + e;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < J; ++j) {
                             const int k = j + 2 * H - i;                   // out(j) reads in(j + 2H - k) of the window
                             if (k >= 0 && k < NT) acc[j] = fma(T[k], v, acc[j]);
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(acc[j], acc[j + 1]);
+                for (int j = 0; j < J; j += 2) *reinterpret_cast<double2 *>(trow + j) = make_double2(acc[j], acc[j + 1]);
             }
             if (mode == PM_CROWDED) {
-                pipe_crowded_masks(p, sm, s, warp, lane, slow, lo_c, hi_c, blk);
+                pipe_crowded_masks(p, sm, s, RW, warp, lane, slow, lo_c, hi_c, blk);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[s]);
-                pipe_bar(2);
-                pipe_crowded_rowdef(sm, slot, rrow, seg, H);
-                pipe_bar(3);                             // (the masks are rewritten by the next crowded block)
+                pipe_bar<GROUP>(2);
+                pipe_crowded_rowdef<J>(sm, slot, rrow, seg, H);
+                pipe_bar<GROUP>(3);                      // (the masks are rewritten by the next crowded block)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.rfull[slot]);
@@ -1043,7 +1058,9 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
 
     // ================= column warps =================
     {
-        const int ccol = tid - PP_GROUP;                 // 0 .. 127
+        const int ct = tid - GROUP;                      // 0 .. GROUP - 1
+        const int ccol = ct & (SP_TX - 1);               // column of the strip
+        const int half = ct >> 7;                        // which J rows of the 16-row output block (0 when J = 16)
         const int cw = ccol >> 5;                        // this warp's 32-column segment
         const int64_t x = x0 + ccol;
         const bool pass = p.passthrough && p.passthrough[c];
@@ -1054,30 +1071,37 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
         const float qall_f = __ull2float_rn(p.qall);
         const double *topf = &sm.top[0][0];
         const uint32_t *rdf = &sm.rowdef[0][0];
+        const int wrow0 = PP_R - H + half * J;           // first window row, counted from the first row of block b - 2
         for (int b = 0; b < nblk; ++b) {
             mbar_wait(&sm.rfull[b % PP_NB], (b / PP_NB) & 1);
             if (b < 2) continue;
             // ring blocks of the window: tb = 0, 1, 2 <-> march blocks b - 2, b - 1, b
             const int s0 = (b - 2) % PP_NB, s1 = (b - 1) % PP_NB, s2 = b % PP_NB;
             const int m0 = sm.mode[s0], m1 = sm.mode[s1], m2 = sm.mode[s2];          // uniform
-            const int64_t yout = y_first + (int64_t)(b - 1) * PP_R;
-            const int nlive = (int)min((int64_t)PP_R, yb - yout);
+            const int64_t yout = y_first + (int64_t)(b - 1) * PP_R + half * J;
+            const int nlive = (int)max((int64_t)0, min((int64_t)J, yb - yout));
             const bool all_blank = m0 == PM_BLANK && m1 == PM_BLANK && m2 == PM_BLANK;
 
-            // ---- numerators: 16 vertically adjacent outputs from 16 + 2H ring rows (window row i <-> row yout - H + i) ----
-            double acc[16];
+            // ---- numerators: J vertically adjacent outputs from J + 2H ring rows (window row i <-> row yout - H + i) ----
+            double acc[J];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            for (int j = 0; j < J; ++j) acc[j] = 0.0;
             if (!all_blank) {
-                // element offsets of the three blocks' first rows in this thread's column (integers: the loads stay LDS)
-                const int o0 = s0 * PP_R * PP_TOP + ccol, o1 = s1 * PP_R * PP_TOP + ccol, o2 = s2 * PP_R * PP_TOP + ccol;
+                // element offsets, in this thread's column, of the 8-row half blocks its window touches (integers: the loads
+                // stay LDS): hb[m] = half block m + half of the three blocks' six
+                int hb[6];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    const int mm = m + half;                               // half = 0 or 1
+                    const int sl = mm < 2 ? s0 : mm < 4 ? s1 : s2;
+                    hb[m] = (sl * PP_R + (mm & 1) * 8) * PP_TOP + ccol;
+                }
 #pragma unroll
                 for (int i = 0; i < NIN; ++i) {
-                    const int rel = PP_R - H + i;                          // row relative to the first row of block b - 2
-                    const int ob = rel < PP_R ? o0 : rel < 2 * PP_R ? o1 : o2;
-                    const double v = topf[ob + (rel % PP_R) * PP_TOP];
+                    const int rel = PP_R - H + i;                          // compile time: row relative to the window's own half-block origin
+                    const double v = topf[hb[rel >> 3] + (rel & 7) * PP_TOP];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < J; ++j) {
                         const int k = j + 2 * H - i;
                         if (k >= 0 && k < NT) acc[j] = fma(T[k], v, acc[j]);
                     }
@@ -1085,9 +1109,9 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
             }
 
             // ---- deficits: exact integers; only the rows that are dirty in this warp's 32 columns are folded in ----
-            unsigned long long def[16];
+            unsigned long long def[J];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) def[j] = 0ull;
+            for (int j = 0; j < J; ++j) def[j] = 0ull;
             bool any_def = false;                                          // uniform
             unsigned long long dirty48 = 0ull;                             // bit 16 tb + r: ring row r of block tb
 #pragma unroll
@@ -1098,9 +1122,9 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     any_def = true;
                     // every row of the block contributes (sum of qx) x qy[k]: prefix sums of qy give the block's share
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        // rows rel = 16 tb .. 16 tb + 15 <-> window rows i = rel - (16 - H) <-> k = j + 2H - i
-                        const int khi = j + 2 * H - (PP_R * tb - (PP_R - H));              // k of the block's first row
+                    for (int j = 0; j < J; ++j) {
+                        // rows rel = 16 tb .. 16 tb + 15 <-> window rows i = rel - wrow0 <-> k = j + 2H - i
+                        const int khi = j + 2 * H - (PP_R * tb - wrow0);                   // k of the block's first row
                         const int klo = khi - (PP_R - 1);                                   // k of its last row
                         const int a = klo < 0 ? 0 : (klo > NT ? NT : klo), e = khi + 1 < 0 ? 0 : (khi + 1 > NT ? NT : khi + 1);
                         if (e > a) def[j] += (unsigned long long)(p.cqy[e] - p.cqy[a]) * p.qsx;
@@ -1109,10 +1133,10 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     dirty48 |= (unsigned long long)sm.dirty[st][cw] << (16 * tb);
                 }
             }
-            // window rows i = rel - (16 - H), i in [0, NIN)
-            unsigned long long todo = (dirty48 >> (PP_R - H)) & ((1ull << NIN) - 1ull);
+            // window rows i = rel - wrow0, i in [0, NIN)
+            unsigned long long todo = (dirty48 >> wrow0) & ((1ull << NIN) - 1ull);
             any_def |= todo != 0ull;
-            if (__popcll(todo) > 10) {
+            if (J == 16 && __popcll(todo) > 10) {
                 // crowded neighbourhood: every row of the non-clean blocks, unrolled (compile-time taps, no loop overhead);
                 // rows of sparse blocks that nothing was scattered into hold zeros
 #pragma unroll
@@ -1123,11 +1147,11 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     const int ord = st * PP_R * SP_TX + ccol;
 #pragma unroll
                     for (int r_in = 0; r_in < PP_R; ++r_in) {
-                        const int i = PP_R * tb + r_in - (PP_R - H);       // window row
+                        const int i = PP_R * tb + r_in - (PP_R - H);       // window row (half = 0 here)
                         if (i < 0 || i >= NIN) continue;
                         const uint32_t d = rdf[ord + r_in * SP_TX];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < J; ++j) {
                             const int k = j + 2 * H - i;
                             if (k >= 0 && k < NT) def[j] += (unsigned long long)d * p.qy[k];
                         }
@@ -1139,21 +1163,21 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
             while (todo) {
                 const int i = __ffsll((long long)todo) - 1;                // uniform
                 todo &= todo - 1ull;
-                const int rel = i + PP_R - H;
+                const int rel = i + wrow0;
                 const int st = (b - 2 + (rel >> 4)) % PP_NB;
                 const uint32_t d = rdf[(st * PP_R + (rel & 15)) * SP_TX + ccol];
                 const uint32_t *q = &sm.qyp[32 + 2 * H - i];               // q[j] = qy[j + 2H - i], zero outside the kernel
 #pragma unroll
-                for (int j = 0; j < 16; ++j) def[j] += (unsigned long long)d * q[j];
+                for (int j = 0; j < J; ++j) def[j] += (unsigned long long)d * q[j];
             }
 
             // ---- epilogue: out = top * qall / present ----
             char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
             const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
-            if (x < p.nx) {
+            if (x < p.nx && nlive > 0) {
                 if (!any_def && !pass) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < J; ++j) {
                         if (j < nlive) {
                             if (OUT64) *reinterpret_cast<double *>(op + j * ostep) = acc[j];
                             else       *reinterpret_cast<float *>(op + j * ostep) = (float)acc[j];
@@ -1161,11 +1185,11 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     }
                 } else if (OUT64) {
 #pragma unroll 1
-                    for (int j0 = 0; j0 < 16; j0 += 1) {
+                    for (int j0 = 0; j0 < J; j0 += 1) {
                         // (float64 output is the rarely used form: compact, register arrays indexed through a switch-free select chain)
                         double a = 0.0; unsigned long long dj = 0ull;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j == j0) { a = acc[j]; dj = def[j]; }
+                        for (int j = 0; j < J; ++j) if (j == j0) { a = acc[j]; dj = def[j]; }
                         if (j0 < nlive) {
                             const unsigned long long present = p.qall - dj;
                             const uint32_t hi = (uint32_t)(present >> 31);
@@ -1180,14 +1204,14 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     // out = top / (1 - x) in float32 (relative error < 5e-7 while x <= 1/2).  More than half of the weight
                     // missing: out = top * qall / present with `present` converted from its 64 bits (same accuracy however
                     // small it is).  Nothing valid at all (present == 0, common inside blank regions) or a plane that is
-                    // copied through: the filled input, fetched in a loop of its own -- it needs neither `acc` nor `def`.
+                    // copied through: the filled input.
                     uint32_t rare = 0u;
                     float *o32 = reinterpret_cast<float *>(op);
                     if (all_blank || pass) {
-                        rare = 0xFFFFu;                                    // (every deficit equals qall there)
-                    } else if (nlive == PP_R) {
+                        rare = (1u << J) - 1u;                             // (every deficit equals qall there)
+                    } else if (nlive == J) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < J; ++j) {
                             const float xdef = (float)(uint32_t)(def[j] >> 31) * inv_q;
                             rare |= xdef > 0.5f ? 1u << j : 0u;
                             *o32 = __fdividef((float)acc[j], 1.0f - xdef);
@@ -1195,7 +1219,7 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < J; ++j) {
                             const float xdef = (float)(uint32_t)(def[j] >> 31) * inv_q;
                             rare |= xdef > 0.5f ? 1u << j : 0u;
                             if (j < nlive) *o32 = __fdividef((float)acc[j], 1.0f - xdef);
@@ -1205,19 +1229,19 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     rare &= (1u << nlive) - 1u;
                     if (rare == (1u << nlive) - 1u) {
                         // every output of this thread is flagged: inside a blank region (or a plane copied through) nothing at
-                        // all is valid under the kernel and the result is the filled input -- 16 INDEPENDENT loads, not a
+                        // all is valid under the kernel and the result is the filled input -- J INDEPENDENT loads, not a
                         // chain of them (the loop below waits a full memory latency per output)
                         bool nothing = true;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) nothing &= def[j] == p.qall;
+                        for (int j = 0; j < J; ++j) nothing &= def[j] == p.qall;
                         if (nothing || pass) {
                             const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
-                            float cv[16];
+                            float cv[J];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) cv[j] = j < nlive ? __ldg(ip + j * p.stride_y) : 0.0f;
+                            for (int j = 0; j < J; ++j) cv[j] = j < nlive ? __ldg(ip + j * p.stride_y) : 0.0f;
                             float *o = reinterpret_cast<float *>(op);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < J; ++j) {
                                 if (j < nlive) {
                                     if (!mask_include_rt(p.mask, cv[j], c, yout + j, x)) cv[j] = p.fill;
                                     o[j * p.out_stride_y] = cv[j];
@@ -1229,10 +1253,10 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     if (rare) {
                         // out of the common path (edges of blank regions): the values move to thread-local arrays so that the
                         // loop over the flagged outputs can index them
-                        float fa[16];
-                        unsigned long long dd[16];
+                        float fa[J];
+                        unsigned long long dd[J];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { fa[j] = (float)acc[j]; dd[j] = def[j]; }
+                        for (int j = 0; j < J; ++j) { fa[j] = (float)acc[j]; dd[j] = def[j]; }
                         const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
                         float *o = reinterpret_cast<float *>(op);
 #pragma unroll 1
@@ -1528,14 +1552,21 @@ static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cuda
     return cudaGetLastError();
 }
 
-template <int H, int OUT64>
-static cudaError_t launch_pipe_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
-    auto kern = sep_pipe_kernel<H, OUT64>;
+template <int H, int OUT64, int J>
+static cudaError_t launch_pipe_j(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    auto kern = sep_pipe_kernel<H, OUT64, J>;
     const size_t smem = sizeof(PipeSmem);
     static unsigned long long configured = 0;        // per instantiation, one bit per device
     if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
-    kern<<<grid, PP_THREADS, smem, s>>>(p);
+    kern<<<grid, 2 * (PP_R * SP_TX / J) + 32, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <int H, int OUT64>
+static cudaError_t launch_pipe_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    // outputs per thread: 16 (4 + 4 compute warps) or 8 (8 + 8); SC_SPATIAL_J overrides the default for experiments
+    if (env_int("SC_SPATIAL_J", PP_DEFAULT_J) == 8) return launch_pipe_j<H, OUT64, 8>(p, grid, s);
+    return launch_pipe_j<H, OUT64, 16>(p, grid, s);
 }
 
 template <int OUT64>

@@ -25,14 +25,21 @@ cases = (("clean shard, 0.1 % NaNs", dict(border=0), False),
          ("top shard of config 4 (102 blank rows + blank side columns)", dict(y0=0, ny_total=4096, nx_total=4096, border=102), False),
          ("interior shard of config 4 (blank side columns)", dict(y0=1024, ny_total=4096, nx_total=4096, border=102), False),
          ("masked > 3 sigma (crowded everywhere)", dict(border=0), True))
-if len(sys.argv) > 1 and sys.argv[1] in ('one', 'one_interior'):
-    dev = synth_cube(nchan, ny, nx, border=0) if sys.argv[1] == 'one' else synth_cube(nchan, ny, nx, y0=1024, ny_total=4096, nx_total=4096, border=102)
-    c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit="K")
+if len(sys.argv) > 1 and sys.argv[1] in ('one', 'one_interior', 'one_edges'):
+    if sys.argv[1] == 'one_edges':
+        nx = 256                                   # two strips, both with the blank frame's 102 side columns
+        dev = synth_cube(nchan * 4, ny, nx, y0=1024, ny_total=4096, nx_total=256, border=102)
+    else:
+        dev = synth_cube(nchan, ny, nx, border=0) if sys.argv[1] == 'one' else synth_cube(nchan, ny, nx, y0=1024, ny_total=4096, nx_total=4096, border=102)
+    c = scb.DaskSpectralCube(dev, benchmark_wcs(dev.shape[0], ny, nx), unit="K")
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     os.environ["SC_SPATIAL_KERNEL"] = "5"
+    if len(sys.argv) > 2:
+        os.environ["SC_SPATIAL_J"] = sys.argv[2]
     for _ in range(3):
         c._run_spatial_smooth(k.array, _lib.F32)
     torch.cuda.synchronize()
+    print("%s: %.2f ms for %d voxels" % (sys.argv[1], timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32)), dev.numel()))
     sys.exit(0)
 for name, kw, masked in cases:
     dev = synth_cube(nchan, ny, nx, **kw)
@@ -40,8 +47,9 @@ for name, kw, masked in cases:
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     if masked:
         c = c.with_mask(c > 3.0)
-    for choice in ("0", "5", "4", "3"):
-        os.environ["SC_SPATIAL_KERNEL"] = choice
+    for choice in ("0", "5", "5j8", "4", "3"):
+        os.environ["SC_SPATIAL_KERNEL"] = choice[0]
+        os.environ["SC_SPATIAL_J"] = "8" if choice.endswith("j8") else "16"
         ms = timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32))
-        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "5": "pipe  ", "4": "sparse(r1)", "3": "march "}[choice], ms), flush=True)
+        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "5": "pipe  ", "5j8": "pipe J=8", "4": "sparse(r1)", "3": "march "}[choice], ms), flush=True)
     del dev, c
