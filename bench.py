@@ -737,7 +737,7 @@ def section_c5(job, line):
                 mode = 'peer'
             except Exception as exc:
                 out['reshard_peer'] = {'unavailable': repr(exc)[:300]}
-            ms_r = job.timeit(lambda: sh.reproject(hdr, reshard_mode=mode), n=2, warm=1)
+            ms_r = job.timeit(lambda: sh.reproject(hdr, reshard_mode=mode), n=3, warm=2)
             out['reproject_sharded'] = {'ms': ms_r, 'reshard': mode, 'what': 'rows->channels re-shard + pixel map + bilinear'}
             out['ms'] = ms_i + ms_r
             out['value'] = V / ((ms_i + ms_r) * 1e-3)
@@ -750,7 +750,7 @@ def section_c5(job, line):
             planes = synth_cube(nloc, ny, nx, seed=SEED + 1, nan_permille=1, border=102)
             cc = isfinite_cube(scb.SpectralCube, planes, w)
             hdr['NAXIS3'] = nloc
-            ms_r = job.timeit(lambda: cc.reproject(hdr), n=3, warm=1)
+            ms_r = job.timeit(lambda: cc.reproject(hdr), n=5, warm=3)       # (the call allocates its 17 GB result: three warm-up calls fill the allocator's cache)
             Vr = nloc * ny * nx
             out['reproject'] = {'ms': ms_r, 'planes_per_gpu': nloc, 'voxels_per_s': Vr * world / (ms_r * 1e-3),
                                 'roofline': job.roof(4 * Vr + 9 * Vr + 16 * ny * nx, ms_r,
