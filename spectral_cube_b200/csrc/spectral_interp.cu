@@ -119,6 +119,19 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
     }
 }
 
+// entry j of the LUT through the read-only path as two 16-byte loads (every thread reads the same sequence: L1-resident)
+__device__ __forceinline__ InterpEntry lut_load(const InterpEntry *lut, int64_t j, int64_t n) {
+    InterpEntry e;
+    if (j >= n) j = n - 1;
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(lut + j));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(lut + j) + 1);
+    e.need = (int32_t)a.x; e.kind = (int32_t)a.y;
+    e.t_lo = __hiloint2double((int)a.w, (int)a.z);
+    e.t_hi = __hiloint2double((int)b.y, (int)b.x);
+    e.pad = 0.0;
+    return e;
+}
+
 // v * 2^-896 as a double, exactly, for finite v; NaN stays NaN and +-inf stays +-inf (see spectral_smooth.cu)
 __device__ __forceinline__ double place_scaled_keep(float v) {
     const int b = __float_as_int(v);
@@ -133,19 +146,21 @@ __device__ __forceinline__ double place_scaled_keep(float v) {
 // slabs of IT_CB channels x 2 KB rows stream through an IT_STAGES-deep ring like in moments.cu, in
 // ascending-axis order (the producer reverses the channel index for descending axes).  Outputs are
 // written as 16-byte vectors (data) and 4-byte vectors (mask).
-constexpr int IT_TILE = 512, IT_CONS = 128, IT_THREADS = IT_CONS + 32, IT_CB = 8, IT_STAGES = 4;
+constexpr int IT_TILE = 512, IT_CONS = 128, IT_THREADS = IT_CONS + 32;
+// ring geometry (channels per slab, slabs in flight): the default and the variants SC_INTERP_RING selects for experiments
 
+template <int IT_CB, int IT_STAGES>
 struct InterpSmem {
     float data[IT_STAGES][IT_CB][IT_TILE];
     uint64_t full[IT_STAGES];
     uint64_t empty[IT_STAGES];
 };
 
-template <int MODE, int OUT64>
-__global__ void __launch_bounds__(IT_THREADS)
+template <int MODE, int OUT64, int IT_CB, int IT_STAGES>
+__global__ void __launch_bounds__(IT_THREADS, (IT_CB * IT_STAGES <= 20 ? 5 : 4))
 spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per_row) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    InterpSmem &sm = *reinterpret_cast<InterpSmem *>(smem_raw);
+    InterpSmem<IT_CB, IT_STAGES> &sm = *reinterpret_cast<InterpSmem<IT_CB, IT_STAGES> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tile = blockIdx.x;
     const int64_t y = tile / tiles_per_row;
@@ -180,72 +195,95 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     const int64_t x = x0 + xo;
     const int64_t plane_out = p.ny * p.nx;
     const int64_t obase = y * p.nx + x;
-    // samples are widened to float64 by bit placement (value x 2^-896, NaN/inf preserved): no conversion
-    // unit on the input side; interpolated values are scaled back with one multiply
-    float cur[4] = {0, 0, 0, 0};
-    double pd[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
-    bool mprev[4] = {false, false, false, false}, mcur[4] = {false, false, false, false};
-    bool any_included[4] = {false, false, false, false};
+    // The two most recent filled samples of each spaxel live in two float32 register sets that swap roles with the
+    // channel's parity (no register moves, the slab height is even); they are widened to float64 only when an output
+    // needs them.  Instruction issue bounds this kernel, not the FP64 pipe (10 % busy): widening every input by bit
+    // placement, as the smoothing kernels do, cost 7 instructions per voxel here for nothing (42 -> see DESIGN.md).
+    float va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+    uint32_t inc_a = 0u, inc_b = 0u;                     // include bits (bit k = spaxel k) of the samples in va / vb
+    uint32_t any_inc = 0u;
     int64_t jj = 0;
-    // the next LUT entry rides in registers, one entry ahead of the output it serves
-    InterpEntry enext = p.lut[0];
+    // the next TWO LUT entries ride in registers: an entry is requested two outputs before it is used (one ahead left
+    // 28 % of the warp samples waiting on that load when an output is due every second channel)
+    InterpEntry enext = lut_load(p.lut, 0, p.nchan_out), enext2 = lut_load(p.lut, 1, p.nchan_out);
     int32_t next_need = p.nchan_out > 0 ? enext.need : -1;
+
+    auto take = [&](float (&dst)[4], uint32_t &inc, int s, int cb, int64_t ch) {
+        const float4 v = *reinterpret_cast<const float4 *>(&sm.data[s][cb][xo]);
+        const float raw[4] = {v.x, v.y, v.z, v.w};
+        inc = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool m = mask_include<MODE>(p.mask, raw[k], ch, y, x + k);
+            dst[k] = m ? raw[k] : p.fill;
+            inc |= (m ? 1u : 0u) << k;
+        }
+        any_inc |= inc;
+    };
+    auto emit = [&](const float (&prev)[4], const float (&cur)[4], uint32_t mp, uint32_t mc, int64_t i) {
+        while (next_need == (int32_t)i) {                                // (the look-ahead keeps the LUT latency off this test)
+            const InterpEntry e = enext;
+            enext = enext2;
+            next_need = jj + 1 < p.nchan_out ? enext.need : -1;
+            enext2 = lut_load(p.lut, jj + 2, p.nchan_out);
+            double r[4];
+            uint32_t m4 = 0u;
+            if (p.mode == 0) {
+                if (e.kind == IK_INTERIOR) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) r[k] = interp_numpy(e.t_lo, e.t_hi, (double)prev[k], (double)cur[k]);
+                    m4 = mp | mc;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) r[k] = (e.kind != IK_KNOT && p.has_fill_value) ? p.fill_value : (double)cur[k];
+                    m4 = mc;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (e.kind == IK_LEFT || e.kind == IK_RIGHT) r[k] = p.has_fill_value ? p.fill_value : nan64();
+                    else r[k] = interp_scipy(e.t_lo, (double)prev[k], (double)cur[k]);
+                    m4 |= (r[k] == r[k] ? 1u : 0u) << k;
+                }
+            }
+            const uint32_t mbits = (m4 * 0x00204081u) & 0x01010101u;     // bit k -> byte k
+            const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
+            const int64_t jm = (p.mode == 1) ? jj : jo;
+            if (active) {
+                if (OUT64) {
+                    double *o = reinterpret_cast<double *>(p.out) + jo * plane_out + obase;
+                    *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
+                    *reinterpret_cast<double2 *>(o + 2) = make_double2(r[2], r[3]);
+                } else {
+                    float *o = reinterpret_cast<float *>(p.out) + jo * plane_out + obase;
+                    *reinterpret_cast<float4 *>(o) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
+                }
+                if (p.out_mask) *reinterpret_cast<uint32_t *>(p.out_mask + jm * plane_out + obase) = mbits;
+            }
+            ++jj;
+        }
+    };
+    static_assert(IT_CB % 2 == 0, "the register sets swap roles with the channel parity");
     for (int it = 0; it < n_iter; ++it) {
         const int s = it % IT_STAGES;
         const int64_t i0 = (int64_t)it * IT_CB;
         const int nch = (int)min((int64_t)IT_CB, p.nchan - i0);
         mbar_wait(&sm.full[s], (it / IT_STAGES) & 1);
-        for (int cb = 0; cb < nch; ++cb) {
-            const int64_t i = i0 + cb;
-            const int64_t ch = p.in_reversed ? p.nchan - 1 - i : i;
-            const float4 v = *reinterpret_cast<const float4 *>(&sm.data[s][cb][xo]);
-            const float raw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                pd[k] = cd[k]; mprev[k] = mcur[k];
-                mcur[k] = mask_include<MODE>(p.mask, raw[k], ch, y, x + k);
-                cur[k] = mcur[k] ? raw[k] : p.fill;
-                cd[k] = place_scaled_keep(cur[k]);
-                any_included[k] |= mcur[k];
-            }
-            while (next_need == (int32_t)i) {                            // (the look-ahead keeps the LUT latency off this test)
-                const InterpEntry e = enext;
-                if (jj + 1 < p.nchan_out) { enext = p.lut[jj + 1]; next_need = enext.need; } else next_need = -1;
-                double r[4];
-                uint32_t mbits = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    bool m;
-                    if (p.mode == 0) {
-                        if (e.kind == IK_INTERIOR) { r[k] = interp_numpy(e.t_lo, e.t_hi, pd[k], cd[k]) * 0x1p+896; m = mprev[k] | mcur[k]; }
-                        else if (e.kind == IK_KNOT) { r[k] = (double)cur[k]; m = mcur[k]; }
-                        else { r[k] = p.has_fill_value ? p.fill_value : (double)cur[k]; m = mcur[k]; }
-                    } else {
-                        if (e.kind == IK_LEFT || e.kind == IK_RIGHT) r[k] = p.has_fill_value ? p.fill_value : nan64();
-                        else r[k] = interp_scipy(e.t_lo, pd[k], cd[k]) * 0x1p+896;
-                        m = r[k] == r[k];
-                    }
-                    mbits |= (m ? 1u : 0u) << (8 * k);
-                }
-                const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
-                const int64_t jm = (p.mode == 1) ? jj : jo;
-                if (active) {
-                    if (OUT64) {
-                        double *o = reinterpret_cast<double *>(p.out) + jo * plane_out + obase;
-                        *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
-                        *reinterpret_cast<double2 *>(o + 2) = make_double2(r[2], r[3]);
-                    } else {
-                        float *o = reinterpret_cast<float *>(p.out) + jo * plane_out + obase;
-                        *reinterpret_cast<float4 *>(o) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
-                    }
-                    if (p.out_mask) *reinterpret_cast<uint32_t *>(p.out_mask + jm * plane_out + obase) = mbits;
-                }
-                ++jj;
+        for (int cb = 0; cb < nch; cb += 2) {
+            const int64_t i = i0 + cb;                                   // even ascending-order channel: into va, vb is the previous one
+            take(va, inc_a, s, cb, p.in_reversed ? p.nchan - 1 - i : i);
+            emit(vb, va, inc_b, inc_a, i);
+            if (cb + 1 < nch) {
+                take(vb, inc_b, s, cb + 1, p.in_reversed ? p.nchan - 2 - i : i + 1);
+                emit(va, vb, inc_a, inc_b, i + 1);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
+    bool any_included[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) any_included[k] = (any_inc >> k) & 1u;
     if (p.mode == 0 && active && (p.fill == p.fill || p.has_fill_value)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -259,13 +297,25 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     }
 }
 
+template <int MODE, int OUT64, int CB, int STAGES>
+static cudaError_t launch_interp_tma_ring(const InterpParams &p, unsigned grid, int tiles_per_row, cudaStream_t s) {
+    auto kern = spectral_interp_tma_kernel<MODE, OUT64, CB, STAGES>;
+    static unsigned long long configured = 0;        // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, sizeof(InterpSmem<CB, STAGES>), &configured)) return e;
+    kern<<<grid, IT_THREADS, sizeof(InterpSmem<CB, STAGES>), s>>>(p, tiles_per_row);
+    return cudaGetLastError();
+}
+
 template <int MODE, int OUT64>
 static cudaError_t launch_interp_tma_one(const InterpParams &p, unsigned grid, int tiles_per_row, cudaStream_t s) {
-    auto kern = spectral_interp_tma_kernel<MODE, OUT64>;
-    static unsigned long long configured = 0;        // per instantiation, one bit per device
-    if (cudaError_t e = ensure_dyn_smem(kern, sizeof(InterpSmem), &configured)) return e;
-    kern<<<grid, IT_THREADS, sizeof(InterpSmem), s>>>(p, tiles_per_row);
-    return cudaGetLastError();
+    // the ring's geometry decides how many CTAs an SM holds: 8 channels x 3 slabs = 48 KB -> 4 CTAs (5.9 ms on a config-5
+    // shard against 7.9 ms with 4 slabs = 3 CTAs); SC_INTERP_RING selects the other shapes for experiments
+    switch (env_int("SC_INTERP_RING", 0)) {
+        case 1:  return launch_interp_tma_ring<MODE, OUT64, 8, 4>(p, grid, tiles_per_row, s);     // 64 KB: 3 CTAs per SM (round 1)
+        case 2:  return launch_interp_tma_ring<MODE, OUT64, 4, 6>(p, grid, tiles_per_row, s);     // finer hand-over, 48 KB
+        case 3:  return launch_interp_tma_ring<MODE, OUT64, 4, 5>(p, grid, tiles_per_row, s);     // 40 KB, 80 registers: 5 CTAs per SM
+        default: return launch_interp_tma_ring<MODE, OUT64, 8, 3>(p, grid, tiles_per_row, s);
+    }
 }
 
 template <int OUT64>

@@ -624,6 +624,38 @@ class BaseSpectralCube(object):
             return self._new_cube_with(data=out)
         return self._new_cube_reporting_f64(out)
 
+    # -- user-function seams (spectral_cube.py:3049-3159; dask_spectral_cube.py:501-638) ------------------------
+    def _apply_function_on_device(self, function, what, **kwargs):
+        """The reference maps a numpy callable over spectra / images on host cores.  Here the cube lives in HBM, so the
+        callable is handed the WHOLE filled cube once, as a float32 CUDA tensor of shape (nchan, ny, nx) -- the dask
+        class's ``accepts_chunks=True`` contract (dask_spectral_cube.py:516-520, 569-574) with the device as the one
+        chunk -- and must return a tensor of the same shape on the same device.  A function that needs numpy arrays
+        cannot run on this path and is refused with that explanation rather than silently pulled to the host."""
+        torch = _torch()
+        for k in ('num_cores', 'verbose', 'use_memmap', 'parallel', 'accepts_chunks', 'return_new_cube', 'save_to_tmp_dir',
+                  'update_function', 'memmap_dir'):
+            kwargs.pop(k, None)
+        data = self._filled_tensor(self._fill_value)
+        try:
+            out = function(data, **kwargs)
+        except TypeError as exc:
+            raise NotImplementedError(
+                "apply_function_parallel_%s: `function` is called once with the filled cube as a float32 CUDA tensor "
+                "(nchan, ny, nx) and must return a tensor of that shape (no CPU fallback): %r" % (what, exc))
+        if not isinstance(out, torch.Tensor) or tuple(out.shape) != tuple(data.shape) or out.device != data.device:
+            raise ValueError("apply_function_parallel_%s: `function` must return a CUDA tensor of shape %s on %s"
+                             % (what, tuple(data.shape), data.device))
+        return self._new_cube_with(data=out.to(torch.float32))
+
+    def apply_function_parallel_spectral(self, function, **kwargs):
+        """Apply ``function`` along the spectral dimension of the filled data; the mask is left unchanged
+        (spectral_cube.py:3103-3159, :3043-3045).  See ``_apply_function_on_device`` for the callable's contract."""
+        return self._apply_function_on_device(function, 'spectral', **kwargs)
+
+    def apply_function_parallel_spatial(self, function, **kwargs):
+        """Apply ``function`` to the channel images of the filled data (spectral_cube.py:3049-3101)."""
+        return self._apply_function_on_device(function, 'spatial', **kwargs)
+
     # -- convolution to a common beam (spectral_cube.py:3335-3392; dask_spectral_cube.py:1412-1464) ------
     @property
     def beam(self):

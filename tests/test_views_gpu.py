@@ -77,3 +77,32 @@ def test_smoothing_a_view_leaves_the_parent_untouched():
     assert_maps_close(got, want, rtol=RTOL, what='smoothed view')
     import torch
     assert torch.equal(torch.nan_to_num(sc._data, nan=-1.0), torch.nan_to_num(before, nan=-1.0))
+
+
+def test_apply_function_parallel_hands_the_filled_cube_to_a_device_function():
+    """spectral_cube.py:3049-3159 / dask :501-638 with the device as the one chunk: the callable gets the FILLED cube as a
+    CUDA tensor and returns one of the same shape; the mask object is left as it is (:3043-3045).  The reference's own
+    use of the seam: tests/test_dask.py:230-252 (a function adding a constant)."""
+    import torch
+    import pytest
+    import numpy as np
+    from tests.helpers import gpu_cube
+    from tests.test_moments_gpu import BENCH_WCS, _random_cube
+    data = _random_cube((6, 5, 8), seed=3, nan_frac=0.1)
+    for use_dask in (False, True):
+        cube = gpu_cube(data, BENCH_WCS, use_dask=use_dask)
+        cube = cube.with_mask(cube > -0.5)
+
+        def func(x, add=None):
+            assert isinstance(x, torch.Tensor) and x.is_cuda and tuple(x.shape) == data.shape
+            return x + add
+        out = cube.apply_function_parallel_spectral(func, add=1, accepts_chunks=True, num_cores=4)
+        want = np.where(np.isfinite(data) & (data > -0.5), data, np.nan) + 1
+        np.testing.assert_array_equal(out.filled_data[:], want.astype(np.float32))
+        assert out.mask is cube.mask and type(out) is type(cube)
+        out2 = cube.apply_function_parallel_spatial(lambda x: torch.flip(x, dims=(2,)))
+        np.testing.assert_array_equal(np.isnan(out2.unmasked_data[:]), np.isnan(want[:, :, ::-1]))
+        with pytest.raises(ValueError, match="must return a CUDA tensor"):
+            cube.apply_function_parallel_spectral(lambda x: x[:2])
+        with pytest.raises(NotImplementedError, match="no CPU fallback"):
+            cube.apply_function_parallel_spectral(lambda x, y: x)
