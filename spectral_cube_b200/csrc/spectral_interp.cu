@@ -24,11 +24,11 @@ int env_int(const char *name, int dflt);
 
 enum { IK_INTERIOR = 0, IK_KNOT = 1, IK_LEFT = 2, IK_RIGHT = 3 };
 
-struct InterpEntry {          // 32 bytes
-    int32_t need;             // highest ascending-order input channel this entry needs
-    int32_t kind;
+struct InterpEntry {          // 32 bytes: the two weights first (one aligned 16-byte load), then need / kind (one 8-byte load)
     double t_lo;              // (x - xlo) / (xhi - xlo): weight of the step from the lower knot
     double t_hi;              // (x - xhi) / (xhi - xlo): the same measured from the upper knot (<= 0)
+    int32_t need;             // highest ascending-order input channel this entry needs
+    int32_t kind;
     double pad;
 };
 
@@ -119,17 +119,14 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
     }
 }
 
-// entry j of the LUT through the read-only path as two 16-byte loads (every thread reads the same sequence: L1-resident)
-__device__ __forceinline__ InterpEntry lut_load(const InterpEntry *lut, int64_t j, int64_t n) {
-    InterpEntry e;
-    if (j >= n) j = n - 1;
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(lut + j));
-    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(lut + j) + 1);
-    e.need = (int32_t)a.x; e.kind = (int32_t)a.y;
-    e.t_lo = __hiloint2double((int)a.w, (int)a.z);
-    e.t_hi = __hiloint2double((int)b.y, (int)b.x);
-    e.pad = 0.0;
-    return e;
+// LUT entry j through the read-only path (every thread reads the same sequence: L1-resident): the weights as one
+// 16-byte load, {need, kind} as one 8-byte load; past the end {-1, 0} -- no channel ever matches
+__device__ __forceinline__ double2 lut_weights(const InterpEntry *lut, int64_t j, int64_t n) {
+    return __ldg(reinterpret_cast<const double2 *>(lut + (j < n ? j : n - 1)));
+}
+__device__ __forceinline__ int2 lut_need_kind(const InterpEntry *lut, int64_t j, int64_t n) {
+    if (j >= n) return make_int2(-1, 0);
+    return __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(lut + j) + 16));
 }
 
 // v * 2^-896 as a double, exactly, for finite v; NaN stays NaN and +-inf stays +-inf (see spectral_smooth.cu)
@@ -203,10 +200,11 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     uint32_t inc_a = 0u, inc_b = 0u;                     // include bits (bit k = spaxel k) of the samples in va / vb
     uint32_t any_inc = 0u;
     int64_t jj = 0;
-    // the next TWO LUT entries ride in registers: an entry is requested two outputs before it is used (one ahead left
-    // 28 % of the warp samples waiting on that load when an output is due every second channel)
-    InterpEntry enext = lut_load(p.lut, 0, p.nchan_out), enext2 = lut_load(p.lut, 1, p.nchan_out);
-    int32_t next_need = p.nchan_out > 0 ? enext.need : -1;
+    // LUT entries ride in registers, requested TWO (weights) and THREE ({need, kind}) outputs before they are used: one
+    // ahead left 28 % of the warp samples waiting on that load when an output is due every second channel.  The weights
+    // of even / odd outputs live in two register pairs that are reloaded in place (a copy would wait for the load).
+    double2 w_even = lut_weights(p.lut, 0, p.nchan_out), w_odd = lut_weights(p.lut, 1, p.nchan_out);
+    int2 nk0 = lut_need_kind(p.lut, 0, p.nchan_out), nk1 = lut_need_kind(p.lut, 1, p.nchan_out), nk2 = lut_need_kind(p.lut, 2, p.nchan_out);
 
     auto take = [&](float (&dst)[4], uint32_t &inc, int s, int cb, int64_t ch) {
         const float4 v = *reinterpret_cast<const float4 *>(&sm.data[s][cb][xo]);
@@ -221,11 +219,12 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
         any_inc |= inc;
     };
     auto emit = [&](const float (&prev)[4], const float (&cur)[4], uint32_t mp, uint32_t mc, int64_t i) {
-        while (next_need == (int32_t)i) {                                // (the look-ahead keeps the LUT latency off this test)
-            const InterpEntry e = enext;
-            enext = enext2;
-            next_need = jj + 1 < p.nchan_out ? enext.need : -1;
-            enext2 = lut_load(p.lut, jj + 2, p.nchan_out);
+        while (nk0.x == (int32_t)i) {
+            InterpEntry e;
+            e.need = nk0.x; e.kind = nk0.y;
+            if (jj & 1) { e.t_lo = w_odd.x; e.t_hi = w_odd.y; w_odd = lut_weights(p.lut, jj + 2, p.nchan_out); }
+            else        { e.t_lo = w_even.x; e.t_hi = w_even.y; w_even = lut_weights(p.lut, jj + 2, p.nchan_out); }
+            nk0 = nk1; nk1 = nk2; nk2 = lut_need_kind(p.lut, jj + 3, p.nchan_out);
             double r[4];
             uint32_t m4 = 0u;
             if (p.mode == 0) {
