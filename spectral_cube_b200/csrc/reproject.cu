@@ -439,6 +439,11 @@ extern "C" int sc_reproject_ex(const float *in, void *out, int out_dtype, float 
         while (tiles * zchunks < 148 * 6 && zchunks * 2 <= nchan && nchan / (zchunks * 2) >= 8) zchunks *= 2;
         if (zchunks > 65535) zchunks = 65535;
         p.chan_per_cta = (int)(cdiv(cdiv(nchan, zchunks), RT_CB) * RT_CB);
+        // channels per CTA also decide what the L2 can do for the overlap of neighbouring tiles' input boxes: a row of output
+        // tiles streams tiles_x * box * chan_per_cta bytes before the next row (whose boxes overlap it) starts
+        const int cap = env_int("SC_REPROJECT_CHAN", 0);
+        if (cap > 0 && p.chan_per_cta > cap) p.chan_per_cta = (int)(cdiv(cap, RT_CB) * RT_CB);
+        SC_CHECK_ARG(cdiv(nchan, p.chan_per_cta) <= 65535, "too many channel chunks");
         dim3 grid((unsigned)cdiv(nx_out, RT), (unsigned)cdiv(ny_out, RT), (unsigned)cdiv(nchan, p.chan_per_cta));
         SC_CHECK_ARG(grid.y <= 65535, "output image too tall for one launch");
         LaunchScope ls(SC_OP_REPROJECT, s);

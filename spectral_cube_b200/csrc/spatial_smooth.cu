@@ -953,6 +953,13 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
             float lo_c = -INFINITY, hi_c = INFINITY;
             if (!slow && p.mask.mode == MODE_INTERVAL) { lo_c = p.lo_closed; hi_c = p.hi_closed; }
             if (t == 0) sm.count[(b + 1) % 3] = 0;       // last read two blocks ago, next written after this block's barrier
+            // the ring slot of this block: free once the column warps have released block b - 4.  Its row-deficit plane is
+            // cleared HERE, ahead of the barrier that follows the widening, so that a sparse block can scatter right after
+            // that barrier (clearing after it cost a second barrier per block)
+            if (b >= PP_NB) mbar_wait(&sm.rempty[slot], ((b / PP_NB) - 1) & 1);
+            for (int i = t; i < PP_R * SP_TX / 4; i += GROUP)
+                *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + (i >> 5)][4 * (i & 31)]) = make_uint4(0u, 0u, 0u, 0u);
+            if (t < 4) sm.dirty[slot][t] = 0u;
             mbar_wait(&sm.full[s], (b / PP_RS) & 1);
 
             // ---- (1) widen every input once: 16 rows x 80 pairs ----
@@ -989,17 +996,11 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[s]);
             }
-            if (b >= PP_NB) mbar_wait(&sm.rempty[slot], ((b / PP_NB) - 1) & 1);
-            if (t < 4) sm.dirty[slot][t] = mode == PM_CROWDED ? 0xFFFFu : 0u;
+            if (t < 4 && mode == PM_CROWDED) sm.dirty[slot][t] = 0xFFFFu;
             if (t == 4) sm.mode[slot] = mode;
 
             // ---- (2) sparse block: scatter the listed inputs' qx[.] into the (zeroed) row-deficit plane ----
             if (mode == PM_SPARSE) {
-                // (clearing the plane here, by the row warps, beats clearing the dirty rows in the column warps when they
-                //  release a block: 8.4 against 8.7 ms -- the column warps are the critical path)
-                for (int i = t; i < PP_R * SP_TX / 4; i += GROUP)
-                    *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + (i >> 5)][4 * (i & 31)]) = make_uint4(0u, 0u, 0u, 0u);
-                pipe_bar<GROUP>(2);
                 for (int e = warp; e < cnt; e += NWARP) {
                     const int ent = sm.list[l3][e];
                     const int r_in = ent >> 8, cin = ent & 255;
