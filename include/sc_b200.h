@@ -229,10 +229,11 @@ int sc_spatial_smooth_sep(const float *in, void *out, int out_dtype,
                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* Denominator strategy of the separable path.  `sc_spatial_smooth_sep` samples the cube itself (every
- * 8th row of up to 16 planes) and lets the device pick between the sparse integer deficit (few missing
- * samples) and the convolved float32 denominator (more than 10 % missing).  A row-sharded job must take
- * ONE decision for all shards to stay bit-identical with the unsharded result: each rank calls
- * `sc_spatial_missing_sample` (counts = device uint32[2] {missing, sampled}, accumulated, not zeroed),
+ * 8-row x 128-column block of up to 16 planes) and lets the device pick between the integer deficit (pipe
+ * kernel) and the convolved float32 denominator (more than a third of the blocks "crowded": over 1/64 of a
+ * block's samples missing, but not all).  A row-sharded job must take ONE decision for all shards to stay
+ * bit-identical with the unsharded result: each rank calls `sc_spatial_missing_sample` (counts = device
+ * uint32[2] {crowded blocks, blocks sampled}, accumulated, not zeroed),
  * sums the counts over the ranks and hands them to `sc_spatial_smooth_sep_ex`. */
 int sc_spatial_missing_sample(const float *in, int64_t nchan, int64_t ny, int64_t nx,
                               int64_t stride_c, int64_t stride_y, const sc_mask_desc *mask,

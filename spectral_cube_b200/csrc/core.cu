@@ -227,7 +227,7 @@ size_t sc_workspace_bytes(int op, int64_t nchan, int64_t ny, int64_t nx, int64_t
         case SC_OP_MOMENTS:         return (size_t)nchan * 24 + 512;          // {d, d^2} table + offsets
         case SC_OP_SMOOTH_MOMENTS:  return (size_t)nchan * 24 + (size_t)aux * 8 + 1024;
         case SC_OP_SPECTRAL_SMOOTH: return (size_t)aux * 8 + 256;             // normalised taps
-        case SC_OP_SPATIAL_SMOOTH:  return (size_t)aux * 8 + (size_t)nchan + 1024;   // taps + pass-through flags
+        case SC_OP_SPATIAL_SMOOTH:  return (size_t)aux * 8 + (size_t)nchan + 2048 + ((size_t)12 << 20) + 4096;   // taps + pass-through flags + the separable kernel's fix-up list (2^19 tiles of 16 bytes) and tile bitmap (4 MiB)
         case SC_OP_SPECTRAL_INTERP: return (size_t)aux * 32 + 256;            // per-output-channel LUT
         default:                    return 256;
     }

@@ -61,6 +61,16 @@ struct SpatialParams {
     uint32_t qsx;                         // sum qx
     double qscale31;                      // qall * 2^(896-31): out = top * qall / present; reciprocal of present >> 31, widened by bit placement
     float lo_closed, hi_closed;          // interval mask as a closed float32 interval
+    // pipe kernel -> fix-up kernel: outputs whose window holds almost nothing valid (0 < present < fix_thresh) are redone
+    // exactly; {count, overflow}, a bit per 32-column x 64-row tile of the output (set by the first column warp that flags an
+    // output in it) and the list of (channel, first row, first column) of the tiles whose bit was set
+    unsigned int *fix_state;
+    uint32_t *fix_list;
+    uint32_t *fix_bitmap;
+    uint32_t fix_cap;
+    int hpad;                            // half-width of the padded taps (2 hpad + 1 entries in ty / tx)
+    int64_t fix_bands, fix_segs;         // tiles per column of the plane, per row
+    unsigned long long fix_thresh;
     const uint8_t *passthrough;          // (nchan) 1 = copy the filled plane through; may be NULL
     const unsigned int *sel;             // {missing, total} of a sample of the cube, or NULL: picks the denominator strategy
     DevMask mask;
@@ -91,13 +101,16 @@ __device__ __forceinline__ double place_scaled_sp(float v) {
     return __hiloint2double(hi, (int)t);
 }
 
-// Strategy switch, decided on the device so that the call stays asynchronous: a sampling kernel counts
-// the missing (excluded or NaN) samples of every 8th row of up to 16 planes; above 10 % the float32
-// denominator convolved alongside the numerator (sep_march_kernel, flat cost) beats the sparse integer
-// deficit (sep_sparse_kernel: 13 % faster on clean data, 1.7x slower when most of the cube is masked).
+// Strategy switch, decided on the device so that the call stays asynchronous: a sampling kernel classifies the
+// 8-row x 128-column blocks of up to 16 planes; a block is CROWDED when more than 1/64 of its samples are missing but
+// not all of them (the pipe kernel then scatters tens of deficits per block or builds them from runs of missing samples:
+// measured 14.5 ms per shard at 1 % scattered NaNs, 22.6 at 3 %, 25 at 40 %; clean or blank blocks cost 8.5).  With more
+// than a third of the blocks crowded the float32 denominator convolved alongside the numerator (sep_march_kernel, flat
+// 17.5 ms) wins.  The round-1 rule counted missing SAMPLES (> 10 %): it sent the shards
+// under config 4's blank frame (25 % missing, nearly all of it in blank blocks) to the march, 16.5 ms instead of 12.
 // Both kernels are launched; the one not selected returns at once.
 __device__ __forceinline__ bool sel_wants_march(const unsigned int *sel) {
-    return (unsigned long long)sel[0] * 10ull > (unsigned long long)sel[1];
+    return (unsigned long long)sel[0] * 3ull > (unsigned long long)sel[1];
 }
 
 __device__ __forceinline__ void compute_bar() {          // barrier among the SP_TX compute threads only
@@ -848,6 +861,228 @@ __device__ __noinline__ void pipe_crowded_rowdef(PipeSmem &sm, int slot, int rro
         *reinterpret_cast<uint4 *>(&sm.rowdef[slot * PP_R + rrow][seg * J + j]) = make_uint4(dx[j], dx[j + 1], dx[j + 2], dx[j + 3]);
 }
 
+// The integer denominator carries the taps quantised to 2^-31.  That is exact enough (< 1e-6) whenever a tap of ordinary size
+// takes part, but an output just inside a blank region -- only the outermost one or two kernel columns / rows reach valid
+// data, present / qall < 2^-13 -- hangs on taps of ~2e-5 whose quantum is 1e-5 of THEM: the weighted mean then misses the
+// reference by up to 2e-5.  Such outputs (two pixels deep along the edges of blank regions) are stored as a NaN with this
+// payload and listed tile by tile; sep_fixup_kernel recomputes them from the input with the float64 taps.
+constexpr uint32_t PP_SENTINEL32 = 0x7FC5CB20u;
+constexpr unsigned long long PP_SENTINEL64 = 0x7FF85CB200000000ull;
+constexpr uint32_t PP_FIX_CAP = 1u << 19;
+
+constexpr int FX_TX = 32, FX_MAXROWS = 64, FX_W = FX_TX + 2 * SP_HP, FX_H = FX_MAXROWS + 2 * SP_HP, FX_THREADS = 128;
+constexpr int FX_WARPS = FX_THREADS / 32, FX_BATCH = 6;                   // window rows a warp has in flight
+constexpr size_t PP_FIX_BITMAP_BYTES = (size_t)4 << 20;                   // 2^25 tiles = 6.9e10 voxels: more than fits the HBM
+
+// Rows [y, y + n) x the 32 columns from xs hold a flagged output: list the 64-row tile(s) they fall into, once each.
+__device__ __forceinline__ void pipe_list_tile(const SpatialParams &p, int64_t c, int64_t y, int n, int64_t xs) {
+    const int64_t seg = xs / FX_TX;
+    for (int64_t band = y / FX_MAXROWS; band <= (y + n - 1) / FX_MAXROWS; ++band) {
+        const int64_t t = (c * p.fix_bands + band) * p.fix_segs + seg;
+        if (t >= (int64_t)(PP_FIX_BITMAP_BYTES * 8)) { p.fix_state[1] = 1u; return; }
+        const uint32_t bit = 1u << (t & 31);
+        if (atomicOr(&p.fix_bitmap[t >> 5], bit) & bit) continue;         // some other warp listed the tile
+        const unsigned int at = atomicAdd(&p.fix_state[0], 1u);
+        if (at < p.fix_cap) *reinterpret_cast<uint4 *>(p.fix_list + 4 * (size_t)at) = make_uint4((uint32_t)c, (uint32_t)(band * FX_MAXROWS), (uint32_t)(seg * FX_TX), 0u);
+        else p.fix_state[1] = 1u;                                         // list full: the fix-up scans the whole output
+    }
+}
+
+// One CTA per listed tile.  The tile's input window is staged ONCE in shared memory with a validity bit mask per window row;
+// the flagged outputs are compacted and each one, four lanes on it, walks ONLY the valid samples of its window with the float64
+// factors -- the exact weighted mean the reference computes (a flagged output has few valid samples by construction).
+// History (config-4 interior shard, 1 million flagged outputs along the blank side columns): a warp per output reading global
+// memory 20 ms; a thread per output position over a staged window 10 ms (5 active threads per instruction); compaction and
+// valid-sample walk 2.1 ms; source row resolved per row instead of per sample 1.6 ms; tiles 64 rows tall instead of 8
+// (the 28 halo rows of the window are amortised) and a rolled staging loop that fits the instruction cache: see DESIGN.md.
+template <int OUT64>
+__device__ __forceinline__ bool fixup_is_flagged(const void *out, int64_t at) {
+    if (OUT64) return reinterpret_cast<const unsigned long long *>(out)[at] == PP_SENTINEL64;
+    return reinterpret_cast<const uint32_t *>(out)[at] == PP_SENTINEL32;
+}
+
+template <int OUT64>
+__global__ void __launch_bounds__(FX_THREADS)
+sep_fixup_kernel(const __grid_constant__ SpatialParams p) {
+    if (p.sel && sel_wants_march(p.sel)) return;
+    const unsigned int listed = p.fix_state[0];
+    const bool overflow = p.fix_state[1] != 0u;
+    if (listed == 0u && !overflow) return;                                // the usual case: nothing to redo
+    __shared__ float win[FX_H][FX_W + 1];
+    __shared__ unsigned long long rmask[FX_H];
+    __shared__ unsigned short flist[FX_MAXROWS * FX_TX];
+    __shared__ int nflag, oy_lo, oy_hi;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int h = p.hpad, nt = 2 * h + 1;
+    const int64_t segs = (p.nx + FX_TX - 1) / FX_TX, bands = (p.ny + FX_MAXROWS - 1) / FX_MAXROWS;
+    const int64_t ntiles = overflow ? p.nchan * bands * segs : (int64_t)min(listed, p.fix_cap);
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t c, y0, xs;
+        if (overflow) {
+            xs = (tile % segs) * FX_TX; const int64_t cb = tile / segs; y0 = (cb % bands) * FX_MAXROWS; c = cb / bands;
+        } else {
+            const uint4 e = *reinterpret_cast<const uint4 *>(p.fix_list + 4 * (size_t)tile);
+            c = e.x; y0 = e.y; xs = e.z;
+        }
+        const int rows = (int)min((int64_t)FX_MAXROWS, p.ny - y0);
+        if (tid == 0) { nflag = 0; oy_lo = FX_MAXROWS; oy_hi = -1; }
+        __syncthreads();                                                  // (also orders the previous tile's reads of `win`)
+        if (xs + lane < p.nx) {
+            const int64_t obase = c * p.out_stride_c + y0 * p.out_stride_y + xs + lane;
+            int lo = FX_MAXROWS, hi = -1;
+            for (int oy = wrp; oy < rows; oy += FX_WARPS)
+                if (fixup_is_flagged<OUT64>(p.out, obase + oy * p.out_stride_y)) {
+                    flist[atomicAdd(&nflag, 1)] = (unsigned short)(oy * FX_TX + lane);
+                    lo = min(lo, oy); hi = max(hi, oy);
+                }
+            if (hi >= 0) { atomicMin(&oy_lo, lo); atomicMax(&oy_hi, hi); }
+        }
+        __syncthreads();
+        const int nf = nflag;
+        if (nf == 0) continue;
+        const int ylo = oy_lo;                                            // only the rows the flagged outputs reach are staged
+        const int64_t ytop = y0 + ylo - h;                                // image row of window row 0
+        {
+            // stage the window a row per warp pass, FX_BATCH rows in flight; the ballots give each row's validity mask (the
+            // window is at most 64 wide).  The row decides where a sample comes from (image, a neighbour shard's halo rows,
+            // zero padding -- a valid sample): resolved once per row, not once per sample.
+            const int nrows = oy_hi - ylo + 1 + 2 * h;
+            const int64_t xa = xs - h + lane, xb = xa + 32;
+            const bool ina = xa >= 0 && xa < p.nx, inb = lane < 2 * h && xb < p.nx;       // (xb >= 0 always: h <= 16)
+            const float *plane = p.in + c * p.stride_c;
+            const int mode = p.mask.mode;
+#pragma unroll 1
+            for (int r0 = wrp; r0 < nrows; r0 += FX_WARPS * FX_BATCH) {
+                float v0[FX_BATCH], v1[FX_BATCH];
+#pragma unroll
+                for (int i = 0; i < FX_BATCH; ++i) {
+                    const int r = r0 + FX_WARPS * i;
+                    const int64_t yy = ytop + r;
+                    const float *src = nullptr;
+                    if (r < nrows) {
+                        if (yy >= 0 && yy < p.ny) src = plane + yy * p.stride_y;
+                        else if (yy < 0 && p.halo_top && yy >= -p.halo_rows) src = p.halo_top + (c * p.halo_rows + (p.halo_rows + yy)) * p.nx;
+                        else if (yy >= p.ny && p.halo_bot && yy < p.ny + p.halo_rows) src = p.halo_bot + (c * p.halo_rows + (yy - p.ny)) * p.nx;
+                    }
+                    v0[i] = (src && ina) ? __ldg(src + xa) : 0.0f;
+                    v1[i] = (src && inb) ? __ldg(src + xb) : 0.0f;
+                }
+                if (mode == MODE_INTERVAL) {
+#pragma unroll
+                    for (int i = 0; i < FX_BATCH; ++i) {
+                        const int64_t yy = ytop + r0 + FX_WARPS * i;
+                        if (yy >= 0 && yy < p.ny) {                       // (halo rows arrive filled)
+                            if (ina && !((v0[i] > p.mask.lo) & (v0[i] < p.mask.hi))) v0[i] = p.fill;
+                            if (inb && !((v1[i] > p.mask.lo) & (v1[i] < p.mask.hi))) v1[i] = p.fill;
+                        }
+                    }
+                } else if (mode != MODE_NONE) {
+#pragma unroll 1
+                    for (int i = 0; i < FX_BATCH; ++i) {
+                        const int64_t yy = ytop + r0 + FX_WARPS * i;
+                        float a = 0.0f, b2 = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < FX_BATCH; ++k) if (k == i) { a = v0[k]; b2 = v1[k]; }
+                        if (yy >= 0 && yy < p.ny) {
+                            if (ina && !eval_mask_generic(p.mask.prog, a, c, yy, xa)) a = p.fill;
+                            if (inb && !eval_mask_generic(p.mask.prog, b2, c, yy, xb)) b2 = p.fill;
+                        }
+#pragma unroll
+                        for (int k = 0; k < FX_BATCH; ++k) if (k == i) { v0[k] = a; v1[k] = b2; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < FX_BATCH; ++i) {
+                    const int r = r0 + FX_WARPS * i;
+                    if (r < nrows) {                                      // (warp-uniform)
+                        const float w1 = lane < 2 * h ? v1[i] : qnan;     // columns past the window: never valid
+                        win[r][lane] = v0[i]; win[r][32 + lane] = w1;
+                        const unsigned m0 = __ballot_sync(0xffffffffu, v0[i] == v0[i]), m1 = __ballot_sync(0xffffffffu, w1 == w1);
+                        if (lane == 0) rmask[r] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // four lanes per output, kernel rows dealt round-robin, two shuffles to combine
+        const int sub = tid & 3;
+        const unsigned long long span = (1ull << nt) - 1ull;              // nt <= 33
+        for (int q0 = 0; q0 < nf; q0 += FX_THREADS / 4) {
+            const int q = q0 + (tid >> 2);
+            const bool active = q < nf;
+            const int o = active ? flist[q] : 0, oy = o / FX_TX, ox = o % FX_TX;
+            double top = 0.0, bot = 0.0;
+            if (active) {
+                for (int ky = sub; ky < nt; ky += 4) {
+                    const int r = oy - ylo + 2 * h - ky;                  // out(y, x) reads in(y + h - ky, x + h - kx)
+                    unsigned long long bits = (rmask[r] >> ox) & span;    // bit j: window column ox + j, tap kx = 2 h - j
+                    if (bits == 0ull) continue;
+                    double t = 0.0, b = 0.0;
+                    while (bits) {
+                        const int j = __ffsll((long long)bits) - 1;
+                        bits &= bits - 1ull;
+                        const double w = p.tx[2 * h - j];
+                        t = fma(w, (double)win[r][ox + j], t); b += w;
+                    }
+                    const double wy = p.ty[ky];
+                    top = fma(wy, t, top); bot = fma(wy, b, bot);
+                }
+            }
+            top += __shfl_xor_sync(0xffffffffu, top, 1); bot += __shfl_xor_sync(0xffffffffu, bot, 1);
+            top += __shfl_xor_sync(0xffffffffu, top, 2); bot += __shfl_xor_sync(0xffffffffu, bot, 2);
+            if (active && sub == 0) {
+                const double res = bot == 0.0 ? (double)win[oy - ylo + h][ox + h] : top / bot;
+                const int64_t at = c * p.out_stride_c + (y0 + oy) * p.out_stride_y + xs + ox;
+                if (OUT64) reinterpret_cast<double *>(p.out)[at] = res;
+                else       reinterpret_cast<float *>(p.out)[at] = (float)res;
+            }
+        }
+    }
+}
+
+// An output whose integer `present` is below fix_thresh: the kernel-row factors are folded again in float64 over the row
+// presences (qsx - rowdef) / qsx.  That is exact whenever the rows that carry the weight are themselves well populated -- the
+// horizontal edge of a blank region: full rows, reached only by the outermost kernel rows -- and the output is finished
+// here.  Where the weight sits on rows with almost nothing valid in them (vertical edges, corners) the quantised kernel-column
+// factors are the problem: *ok = false, and the output goes to sep_fixup_kernel.
+template <int H>
+__device__ __noinline__ double pipe_present_f64(const SpatialParams &p, const uint32_t *rdf, int b, int wrow0, int j0,
+                                                int m0, int m1, int m2, int ccol, bool *ok) {
+    // (the column warps pace the pipeline: along a VERTICAL edge two lanes of every block come here, and a full fold for each
+    // of them cost 8 ms per shard.  One look at the outermost rows of the window tells the two cases apart.)
+    *ok = false;
+    {
+        bool full_row = false;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int rel = j0 + (e ? 2 * H : 0) + wrow0, tb = rel >> 4;
+            const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
+            if (mt == PM_BLANK) continue;
+            const uint32_t d = mt == PM_CLEAN ? 0u : rdf[(((b - 2 + tb) % PP_NB) * PP_R + (rel & 15)) * SP_TX + ccol];
+            full_row |= d < (p.qsx >> 1);
+        }
+        if (!full_row) return 0.0;
+    }
+    double P = 0.0, E = 0.0;
+    const double inv_qsx = 1.0 / (double)p.qsx;
+    const uint32_t tiny = p.qsx >> 11;
+    for (int k = 0; k <= 2 * H; ++k) {
+        const int rel = j0 + 2 * H - k + wrow0;                            // row counted from the first row of block b - 2
+        const int tb = rel >> 4;
+        const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
+        if (mt == PM_BLANK) continue;
+        uint32_t d = 0u;
+        if (mt != PM_CLEAN) d = rdf[(((b - 2 + tb) % PP_NB) * PP_R + (rel & 15)) * SP_TX + ccol];
+        const uint32_t pres = p.qsx - d;
+        const double w = p.ty[k] * ((double)pres * inv_qsx);
+        P += w;
+        if (pres < tiny) E += w;
+    }
+    *ok = P > 0.0 && E * 1024.0 <= P;
+    return P;
+}
+
 // J = outputs per thread in both passes: 16 -> 4 row warps + 4 column warps (fewest shared-memory loads per output),
 // 8 -> 8 + 8 (two warps per role and scheduler: more latency hiding, 1.6x the shared-memory traffic of the passes)
 template <int H, int OUT64, int J>
@@ -1173,6 +1408,7 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
             }
 
             // ---- epilogue: out = top * qall / present ----
+            bool flagged = false;                                          // some output of this thread goes to the fix-up kernel
             char *op = reinterpret_cast<char *>(p.out) + (OUT64 ? 8 : 4) * (c * p.out_stride_c + yout * p.out_stride_y + x);
             const int64_t ostep = (OUT64 ? 8 : 4) * p.out_stride_y;
             if (x < p.nx && nlive > 0) {
@@ -1195,7 +1431,13 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                             const unsigned long long present = p.qall - dj;
                             const uint32_t hi = (uint32_t)(present >> 31);
                             double res;
-                            if (hi < (1u << 24) || pass) res = sparse_rare_output(p, a, present, pass, c, yout + j0, x);
+                            bool ok = false;
+                            double pf = 1.0;
+                            const bool low = present != 0ull && present < p.fix_thresh && !pass;
+                            if (low) pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
+                            if (low && ok) res = a / pf;
+                            else if (low) { res = __longlong_as_double((long long)PP_SENTINEL64); flagged = true; }
+                            else if (hi < (1u << 24) || pass) res = sparse_rare_output(p, a, present, pass, c, yout + j0, x);
                             else res = dj != 0ull ? a * (place_scaled_sp(__frcp_rn((float)hi)) * p.qscale31) : a;
                             *reinterpret_cast<double *>(op + j0 * ostep) = res;
                         }
@@ -1260,6 +1502,13 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                         for (int j = 0; j < J; ++j) { fa[j] = (float)acc[j]; dd[j] = def[j]; }
                         const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
                         float *o = reinterpret_cast<float *>(op);
+                        // outputs with almost nothing valid: along a HORIZONTAL edge most lanes of the warp hold some and the
+                        // float64 re-fold (all lanes busy) settles them here; along a vertical edge it is two lanes, which go
+                        // straight to the fix-up kernel (any answer of this vote is correct, it only picks the cheaper way)
+                        bool lowany = false;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) lowany |= dd[j] != p.qall && p.qall - dd[j] < p.fix_thresh;
+                        const bool wide = __popc(__ballot_sync(__activemask(), lowany)) >= 8;
 #pragma unroll 1
                         while (rare) {
                             const int j0 = __ffs((int)rare) - 1;
@@ -1269,6 +1518,12 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                             if (present == 0ull || pass) {
                                 r = __ldg(ip + j0 * p.stride_y);
                                 if (!mask_include_rt(p.mask, r, c, yout + j0, x)) r = p.fill;
+                            } else if (present < p.fix_thresh) {
+                                bool ok = false;
+                                double pf = 1.0;
+                                if (wide) pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
+                                if (ok) r = (float)((double)fa[j0] / pf);
+                                else { r = __uint_as_float(PP_SENTINEL32); flagged = true; }   // redone exactly by sep_fixup_kernel
                             } else {
                                 r = fa[j0] * __fdividef(qall_f, __ull2float_rn(present));
                             }
@@ -1277,6 +1532,7 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                     }
                 }
             }
+            if (__ballot_sync(0xffffffffu, flagged) && lane == 0) pipe_list_tile(p, c, yout, nlive, x0 + 32 * cw);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.rempty[s0]);
         }
@@ -1511,22 +1767,39 @@ static int maybe_passthrough_flags(SpatialParams &p, int plane_passthrough, void
     return SC_OK;
 }
 
+// One warp per sampled block (8 rows x 128 columns, the pipe kernel's unit of work) of up to 16 planes: sel[0] counts the
+// CROWDED blocks -- more than 1/64 of the samples missing, but not all of them -- and sel[1] the blocks seen.
 __global__ void __launch_bounds__(256)
 missing_sample_kernel(const __grid_constant__ SpatialParams p, unsigned int *sel) {
     const int64_t cstep = max((int64_t)1, p.nchan / 16);
-    const int64_t ncs = (p.nchan + cstep - 1) / cstep, nys = (p.ny + 7) / 8;
-    const int64_t total = ncs * nys * p.nx;
-    unsigned int miss = 0, seen = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t x = i % p.nx, r = i / p.nx;
-        const int64_t y = (r % nys) * 8, c = (r / nys) * cstep;
-        const float v = __ldg(p.in + c * p.stride_c + y * p.stride_y + x);
-        miss += (v != v || !mask_include_rt(p.mask, v, c, y, x)) ? 1u : 0u;
+    const int64_t ncs = (p.nchan + cstep - 1) / cstep, bands = (p.ny + 7) / 8, strips = (p.nx + 127) / 128;
+    const int64_t total = ncs * bands * strips;
+    const int lane = threadIdx.x & 31;
+    unsigned int crowded = 0, seen = 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t x0 = (i % strips) * 128, r = i / strips;
+        const int64_t y0 = (r % bands) * 8, c = (r / bands) * cstep;
+        unsigned int miss = 0, n = 0;
+        float v[32];                                                      // all 32 loads in flight before the mask is evaluated
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int64_t y = y0 + (j >> 2), x = x0 + 32 * (j & 3) + lane;
+            v[j] = (y < p.ny && x < p.nx) ? __ldg(p.in + c * p.stride_c + y * p.stride_y + x) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int64_t y = y0 + (j >> 2), x = x0 + 32 * (j & 3) + lane;
+            if (y < p.ny && x < p.nx) {
+                miss += (v[j] != v[j] || !mask_include_rt(p.mask, v[j], c, y, x)) ? 1u : 0u;
+                n += 1u;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { miss += __shfl_xor_sync(0xffffffffu, miss, d); n += __shfl_xor_sync(0xffffffffu, n, d); }
+        crowded += (miss * 64u > n && miss < n) ? 1u : 0u;
         seen += 1u;
     }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) { miss += __shfl_xor_sync(0xffffffffu, miss, d); seen += __shfl_xor_sync(0xffffffffu, seen, d); }
-    if ((threadIdx.x & 31) == 0 && seen) { atomicAdd(&sel[0], miss); atomicAdd(&sel[1], seen); }
+    if (lane == 0 && seen) { atomicAdd(&sel[0], crowded); atomicAdd(&sel[1], seen); }
 }
 
 template <int H, int OUT64>
@@ -1554,17 +1827,26 @@ static cudaError_t launch_sparse_one(const SpatialParams &p, unsigned grid, cuda
 }
 
 template <int H, int OUT64, int J>
-static cudaError_t launch_pipe_j(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+static cudaError_t launch_pipe_j(SpatialParams p, unsigned grid, cudaStream_t s) {
     auto kern = sep_pipe_kernel<H, OUT64, J>;
     const size_t smem = sizeof(PipeSmem);
     static unsigned long long configured = 0;        // per instantiation, one bit per device
     if (cudaError_t e = ensure_dyn_smem(kern, smem, &configured)) return e;
+    p.hpad = H;
+    p.fix_bands = (p.ny + FX_MAXROWS - 1) / FX_MAXROWS;
+    p.fix_segs = (p.nx + FX_TX - 1) / FX_TX;
+    const size_t tiles = (size_t)(p.nchan * p.fix_bands * p.fix_segs);
+    if (cudaError_t e = cudaMemsetAsync(p.fix_state, 0, 8, s)) return e;
+    if (cudaError_t e = cudaMemsetAsync(p.fix_bitmap, 0, std::min(PP_FIX_BITMAP_BYTES, (tiles / 32 + 1) * 4), s)) return e;
     kern<<<grid, 2 * (PP_R * SP_TX / J) + 32, smem, s>>>(p);
+    if (cudaError_t e = cudaGetLastError()) return e;
+    sep_fixup_kernel<OUT64><<<148 * 12, FX_THREADS, 0, s>>>(p);            // returns at once when nothing was listed
     return cudaGetLastError();
 }
 
 template <int H, int OUT64>
 static cudaError_t launch_pipe_one(const SpatialParams &p, unsigned grid, cudaStream_t s) {
+    if (p.fix_state == nullptr) return cudaErrorInvalidValue;             // (the entry point sized the workspace for it)
     // outputs per thread: 16 (4 + 4 compute warps) or 8 (8 + 8); SC_SPATIAL_J overrides the default for experiments
     if (env_int("SC_SPATIAL_J", PP_DEFAULT_J) == 8) return launch_pipe_j<H, OUT64, 8>(p, grid, s);
     return launch_pipe_j<H, OUT64, 16>(p, grid, s);
@@ -1739,6 +2021,21 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
             missing_sample_kernel<<<148 * 2, 256, 0, s>>>(p, sel);
             SC_CUDA(cudaGetLastError());
             p.sel = sel;
+        }
+        // the pipe kernel's fix-up list lives behind the taps, the strategy counters and the pass-through flags
+        const size_t fix_off = (((size_t)ntaps_y * ntaps_x * 8 + 512 + (size_t)nchan + 256) + 255) & ~(size_t)255;
+        p.fix_state = nullptr; p.fix_list = nullptr; p.fix_bitmap = nullptr; p.fix_cap = 0;
+        p.fix_thresh = p.qall >> 13;
+        if (nonneg && choice != 3 && choice != 4) {
+            const size_t need = fix_off + 256 + (size_t)PP_FIX_CAP * 16 + PP_FIX_BITMAP_BYTES;
+            if (!workspace || workspace_bytes < need) {
+                set_error("workspace too small: need %zu bytes, got %zu (sc_workspace_bytes(SC_OP_SPATIAL_SMOOTH, ...))", need, workspace_bytes);
+                return SC_ERR_WORKSPACE;
+            }
+            p.fix_state = (unsigned int *)((uint8_t *)workspace + fix_off);
+            p.fix_list = (uint32_t *)((uint8_t *)workspace + fix_off + 256);
+            p.fix_bitmap = (uint32_t *)((uint8_t *)workspace + fix_off + 256 + (size_t)PP_FIX_CAP * 16);
+            p.fix_cap = PP_FIX_CAP;
         }
         LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
         cudaError_t e = cudaSuccess;

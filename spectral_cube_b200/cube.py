@@ -566,8 +566,8 @@ class BaseSpectralCube(object):
         return None
 
     def _spatial_strategy_counts(self):
-        """Device uint32[2] {missing, sampled} of this cube's rows: what the separable spatial kernels use to
-        pick their denominator strategy.  Row-sharded jobs sum it over the ranks (distributed.py)."""
+        """Device uint32[2] {crowded blocks, blocks sampled} of this cube's rows: what the separable spatial
+        kernels use to pick their denominator strategy.  Row-sharded jobs sum it over the ranks (distributed.py)."""
         torch = _torch()
         lib = _lib.load()
         src = self._data

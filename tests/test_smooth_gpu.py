@@ -208,11 +208,26 @@ def test_spatial_smooth_gaussian_matches_oracle(sigma, use_dask):
     assert_maps_close(got, want, rtol=RTOL, what='sigma=%g' % sigma)
 
 
+# the separable kernels the library can be told to run (SC_SPATIAL_KERNEL / SC_SPATIAL_J): "auto" picks the pipelined kernel
+# or, with more than a third of the 8 x 128 blocks crowded with missing samples, the convolved-denominator march -- forcing each one keeps every denominator path under test
+SEPARABLE_KERNELS = {'auto': (None, None), 'pipe_j8': ('5', '8'), 'pipe_j16': ('5', '16'), 'sparse_r1': ('4', None), 'march': ('3', None)}
+
+
+def _force_kernel(monkeypatch, name):
+    kern, j = SEPARABLE_KERNELS[name]
+    if kern is not None:
+        monkeypatch.setenv('SC_SPATIAL_KERNEL', kern)
+    if j is not None:
+        monkeypatch.setenv('SC_SPATIAL_J', j)
+
+
+@pytest.mark.parametrize('kernel', sorted(SEPARABLE_KERNELS))
 @pytest.mark.parametrize('sigma', [1.0, 8 / 2.3548200450309493])
-def test_spatial_smooth_blank_bands_and_crowded_blocks(sigma):
-    """The three denominator paths of the sparse separable kernel in one image: isolated NaNs (listed
-    inputs), a half-masked region (crowded blocks: integer convolution of the flags) and a blank band
-    wider than a CTA's 8 x 160 window (closed form; outputs deep inside keep the filled input)."""
+def test_spatial_smooth_blank_bands_and_crowded_blocks(sigma, kernel, monkeypatch):
+    """The denominator paths of the separable kernels in one image: isolated NaNs (listed inputs -> scattered row
+    deficits), a half-masked region (crowded blocks: deficits from the runs of missing samples / integer convolution of
+    the flags) and a blank band wider than a CTA's window (closed form; outputs deep inside keep the filled input)."""
+    _force_kernel(monkeypatch, kernel)
     scb = _kernels()
     rng = np.random.default_rng(int(sigma * 100))
     data = _random_cube((2, 96, 640), seed=int(sigma * 7), nan_frac=0.002)
@@ -224,6 +239,29 @@ def test_spatial_smooth_blank_bands_and_crowded_blocks(sigma):
     want = oc.spatial_smooth(oconv.Gaussian2DKernel(sigma))._data
     assert np.isnan(want[:, 45:50, 200:400]).all()                            # deep inside the band: nothing valid
     assert_maps_close(got, want, rtol=RTOL, what='sigma=%g' % sigma)
+
+
+@pytest.mark.parametrize('kernel', ['pipe_j8', 'pipe_j16', 'march'])
+@pytest.mark.parametrize('use_dask', [False, True])
+def test_spatial_smooth_benchmark_block_matches_oracle(kernel, use_dask, monkeypatch):
+    """Config 4's smoothing (29 x 29 Gaussian, FWHM 8 px) on a block of the benchmark cube that holds everything the
+    full cube does: 4096-pixel rows (32 strips, the outer two clipped by the image and holding the blank frame's 102
+    side columns), the frame's last rows (blank blocks, then a crowded one), 0.1 % NaNs -- against the astropy
+    restatement (spectral_cube.py:2808-2842, dask :962-993)."""
+    _force_kernel(monkeypatch, kernel)
+    scb = _kernels()
+    from spectral_cube_b200.synth import synth_cube
+    from oracle.synth import synth_block
+    ny, nx, y0 = 72, 4096, 60                              # rows 60 .. 131 of the 4096-row image: 42 blank rows, then data
+    dev = synth_cube(1, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    host = synth_block(1, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), host.view(np.uint32))
+    sc, oc = gpu_cube(dev, BENCH_WCS, use_dask=use_dask), oracle_cube(host, BENCH_WCS, use_dask=use_dask)
+    got = sc.spatial_smooth(scb.Gaussian2DKernel(8 / 2.3548200450309493)).unmasked_data[:]
+    want = oc.spatial_smooth(oconv.Gaussian2DKernel(8 / 2.3548200450309493))._data
+    # (local rows < 14 see the zero padding above the block -- valid samples -- and come out as zeros)
+    assert np.isnan(want[0, 15:25, 200:3800]).all() and np.isfinite(want[0, 60:, 200:3800]).all()
+    assert_maps_close(got, want, rtol=RTOL, what='config-4 block, %s' % kernel)
 
 
 def test_spatial_smooth_elliptical_and_nonseparable_match_oracle():
@@ -275,7 +313,7 @@ def test_spatial_smooth_row_shards_with_halos_equal_the_whole_image():
     halo_for_bot = pack(top, 40 - h, h)                  # the rows just above the bottom shard
     # one denominator strategy for all shards: the job-wide sample (here: the shards' counts summed)
     counts = top._spatial_strategy_counts() + bot._spatial_strategy_counts()
-    assert torch.equal(counts, whole._spatial_strategy_counts())          # 40 rows: both shards start on a sampled row
+    assert torch.equal(counts, whole._spatial_strategy_counts())          # 40 rows: the shards' 8-row sample blocks are the whole cube's
     a = top._run_spatial_smooth(k.array, _lib.F32, halo_top=None, halo_bot=halo_for_top, halo_rows=h, strategy_counts=counts)
     b = bot._run_spatial_smooth(k.array, _lib.F32, halo_top=halo_for_bot, halo_bot=None, halo_rows=h, strategy_counts=counts)
     got = torch.cat([a, b], dim=1)

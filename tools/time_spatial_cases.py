@@ -41,15 +41,30 @@ if len(sys.argv) > 1 and sys.argv[1] in ('one', 'one_interior', 'one_edges'):
     torch.cuda.synchronize()
     print("%s: %.2f ms for %d voxels" % (sys.argv[1], timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32)), dev.numel()))
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == 'sweep':            # scattered NaNs at rising density: where does the march win?
+    for permille in (10, 30, 60, 100, 200, 400):
+        dev = synth_cube(nchan, ny, nx, border=0, nan_permille=permille)
+        c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit="K")
+        c._mask = scb.LazyMask(np.isfinite, cube=c)
+        line = "scattered NaNs %4.1f %%:" % (permille / 10)
+        for choice in ("0", "5", "3"):
+            os.environ["SC_SPATIAL_KERNEL"] = choice
+            os.environ.pop("SC_SPATIAL_J", None)
+            line += "  %s %.2f ms" % ({"0": "auto", "5": "pipe", "3": "march"}[choice], timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32)))
+        print(line, "  counts", c._spatial_strategy_counts().tolist(), flush=True)
+        del dev, c
+    sys.exit(0)
 for name, kw, masked in cases:
     dev = synth_cube(nchan, ny, nx, **kw)
     c = scb.DaskSpectralCube(dev, benchmark_wcs(nchan, ny, nx), unit="K")
     c._mask = scb.LazyMask(np.isfinite, cube=c)
     if masked:
         c = c.with_mask(c > 3.0)
-    for choice in ("0", "5", "5j8", "4", "3"):
+    for choice in ("0", "5j16", "5j8", "4", "3"):
         os.environ["SC_SPATIAL_KERNEL"] = choice[0]
-        os.environ["SC_SPATIAL_J"] = "8" if choice.endswith("j8") else "16"
+        os.environ.pop("SC_SPATIAL_J", None)                      # "auto" is the library's own choice of kernel and of J
+        if choice.startswith("5j"):
+            os.environ["SC_SPATIAL_J"] = choice[2:]
         ms = timeit(lambda: c._run_spatial_smooth(k.array, _lib.F32))
-        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "5": "pipe  ", "5j8": "pipe J=8", "4": "sparse(r1)", "3": "march "}[choice], ms), flush=True)
+        print("%-62s kernel=%s  %.2f ms" % (name, {"0": "auto  ", "5j16": "pipe J=16", "5j8": "pipe J=8", "4": "sparse(r1)", "3": "march "}[choice], ms), flush=True)
     del dev, c
