@@ -684,7 +684,7 @@ def section_c4_strong(job, line):
     for mode in modes:
         ms = job.timeit(lambda: sh.spatial_smooth(k, halo_mode='p2p' if mode == 'none' else mode), n=3, warm=1)
         out['halo_' + mode] = {'ms': ms, 'voxels_per_s': V / (ms * 1e-3),
-                               'roofline': job.roof(8 * V // world, ms, 'sep_sparse_kernel / sep_march_kernel<14> (29x29 separable)',
+                               'roofline': job.roof(8 * V // world, ms, 'sep_pipe_kernel<14> + sep_fixup_kernel (29x29 separable; sep_march_kernel when the sample says crowded)',
                                                     note='FP64-pipe bound: 58 DFMA per voxel; floor at 15.8 TDFMA/s = %.1f ms per GPU'
                                                          % (58.0 * V / world / 15.8e12 * 1e3))}
     out['gpu_launches'] = int(job.lib.sc_launch_count() - n0)
@@ -764,6 +764,19 @@ def section_c5(job, line):
             hdr['NAXIS3'] = nloc
             ms_r = job.timeit(lambda: cc.reproject(hdr), n=5, warm=3)       # (the call allocates its 17 GB result: three warm-up calls fill the allocator's cache)
             Vr = nloc * ny * nx
+            # the two device parts on their own (diagnostic: the public call adds header parsing and allocation on the host)
+            from spectral_cube_b200.wcs import as_cube_wcs
+            neww = as_cube_wcs(hdr)
+            ms_map = job.timeit(lambda: cc._pixel_map(neww, ny, nx), n=3, warm=1)
+            yin, xin = cc._pixel_map(neww, ny, nx)
+            ms_kern = job.timeit(lambda: cc._run_reproject(yin, xin, 1), n=3, warm=2)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                cc.reproject(hdr)
+            job.torch.cuda.synchronize()
+            out['reproject_parts'] = {'pixel_map_ms': ms_map, 'bilinear_kernel_ms': ms_kern,
+                                      'public_call_wall_ms': (time.perf_counter() - t0) / 3 * 1e3}
+            del yin, xin
             out['reproject'] = {'ms': ms_r, 'planes_per_gpu': nloc, 'voxels_per_s': Vr * world / (ms_r * 1e-3),
                                 'roofline': job.roof(4 * Vr + 9 * Vr + 16 * ny * nx, ms_r,
                                                      'wcs_pixel_map_kernel + reproject_tiled_kernel (f64 + footprint out; the float32 '
@@ -831,6 +844,7 @@ def run_ours(args):
     job = Job(args)
     line = {}
     section_headline(job, line)
+    line['hbm_held_after_GB'] = {'headline': round(job.torch.cuda.memory_allocated() / 1e9, 2)}   # tensors still referenced
     sections = [('c3', section_c3, args.no_c3 or job.world > 1), ('c4_strong', section_c4_strong, args.no_c4),
                 ('c5', section_c5, args.no_c5 or job.world in (2,)), ('target_strong', section_target_strong, args.no_target),
                 ('selftest', section_selftest, args.no_selftest or job.world < 2)]
@@ -842,6 +856,7 @@ def run_ours(args):
             fn(job, line)
             if isinstance(line.get(name), dict):
                 line[name]['section_wall_s'] = round(time.perf_counter() - t0, 2)
+            line['hbm_held_after_GB'][name] = round(job.torch.cuda.memory_allocated() / 1e9, 2)
         except Exception as exc:                      # never lose the headline to an extra
             line[name] = {'error': repr(exc)[:400]}
             try:

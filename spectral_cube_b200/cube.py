@@ -1146,7 +1146,10 @@ class _PendingFloat32Copy(object):
     def __init__(self, hi):
         self.hi = hi
         self.shape = tuple(hi.shape)
-        self.source = self                 # `.source._data.device` is where the cube lives
+
+    @property
+    def source(self):                       # `.source._data.device` is where the cube lives.  (A property, not an attribute
+        return self                         # holding `self`: that cycle kept the 17 GB result until the cyclic GC came by.)
 
     @property
     def _data(self):
