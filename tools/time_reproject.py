@@ -18,7 +18,7 @@ def ev(f, n=3):
     f(); torch.cuda.synchronize()
     a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); a_.record()
-    for _ in range(n): r = f()
+    for _ in range(n): f()          # (do not keep the result: a second 17 GB block would be cudaMalloc'ed inside the timed region)
     b_.record(); torch.cuda.synchronize()
     return a_.elapsed_time(b_) / n, (time.perf_counter() - t0) / n * 1e3
 neww = as_cube_wcs(hdr)
