@@ -571,7 +571,7 @@ def section_headline(job, line):
             k17 = scb.Gaussian1DKernel(5 * FWHM2SIGMA).array
             sm_out = torch.empty_like(dev)
             ms = job.timeit(lambda: iso._run_spectral_smooth(k17, _lib.F32, out=sm_out), n=5, warm=2)
-            tr, tf = ncu_traffic('r02_spectral_smooth_ncu_full.txt', 'smooth_tma_kernel')
+            tr, tf = ncu_traffic('r02_spectral_smooth_kernel_ncu_full.txt', 'smooth_tma_kernel')
             if tr is None:
                 tr, tf = ncu_traffic('r01_spectral_smooth_ncu_full_v11.txt', 'smooth_tma_kernel')
             line['spectral_smooth'] = {'ms': ms, 'voxels_per_s': world * voxels / (ms * 1e-3),
