@@ -319,6 +319,23 @@ int sc_spectral_interp(const float *in, void *out, int out_dtype, uint8_t *out_m
                        int in_reversed, int out_reversed, int mode,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same interpolation with a SCATTERED output (the step between `spectral_interpolate` and `reproject`
+ * of a row-sharded cube, which needs whole planes): output channel j of these rows is stored at
+ * `(T *)out_chan_ptrs[j] + y * nx + x`.  `out_chan_ptrs` is a DEVICE array of nchan_out addresses, each 16-byte aligned
+ * and pointing at row `y0` of channel j in the buffer of the rank that owns that channel -- this rank's own buffer or a
+ * peer's mapped over NVLink (torch symmetric memory `buffer_ptrs`).  The interpolation kernel's stores ARE the exchange:
+ * no row-sharded result is written and read again, no all-to-all follows.  The caller brackets the call with a barrier
+ * among the ranks on both sides.  `out_mask` (may be NULL) stays local, (nchan_out, ny, nx). */
+int sc_spectral_interp_scatter(const float *in, const uint64_t *out_chan_ptrs, int out_dtype, uint8_t *out_mask,
+                               int64_t nchan, int64_t ny, int64_t nx,
+                               int64_t stride_c, int64_t stride_y,
+                               int64_t nchan_out,
+                               const sc_mask_desc *mask, double fill,
+                               const double *in_axis, const double *grid,
+                               int has_fill_value, double fill_value,
+                               int in_reversed, int out_reversed, int mode,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- reprojection ----------------------------------------------------------------------
  * Replaces `reproject_interp((data, header), wcs_out, shape_out=..., order='bilinear')`
  * (spectral_cube.py:2726-2732): per output pixel the input pixel position (float64 planes

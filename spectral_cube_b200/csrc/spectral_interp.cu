@@ -42,8 +42,18 @@ struct InterpParams {
     int has_fill_value;
     double fill_value;
     int in_reversed, out_reversed, mode;
+    // scatter form (row-sharded cube -> channel shards): output channel j of THIS rank's rows is stored at
+    // out_chan_ptrs[j] + y * nx + x -- a pointer into the buffer of the rank that owns channel j, local or a peer's
+    // over NVLink -- instead of out + (j * ny + y) * nx + x
+    const uint64_t *out_chan_ptrs;
     DevMask mask;
 };
+
+template <typename T>
+__device__ __forceinline__ T *interp_out_row(const InterpParams &p, int64_t j, int64_t plane_out) {
+    if (p.out_chan_ptrs) return reinterpret_cast<T *>(__ldg(p.out_chan_ptrs + j));
+    return reinterpret_cast<T *>(p.out) + j * plane_out;
+}
 
 // numpy/_core/src/multiarray/compiled_base.c (arr_interp): interior sample between two knots
 // (numpy: slope = (f1-f0)/(xhi-xlo); r = slope*(x-xlo) + f0; if NaN: slope*(x-xhi) + f1; if still NaN and
@@ -102,8 +112,8 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
             const int64_t jo = p.out_reversed ? p.nchan_out - 1 - jj : jj;
             // dask: the mask is taken BEFORE the output is flipped back (dask_spectral_cube.py:1364-1367)
             const int64_t jm = (p.mode == 1) ? jj : jo;
-            if (OUT64) reinterpret_cast<double *>(p.out)[jo * plane_out + obase] = r;
-            else       reinterpret_cast<float *>(p.out)[jo * plane_out + obase] = (float)r;
+            if (OUT64) interp_out_row<double>(p, jo, plane_out)[obase] = r;
+            else       interp_out_row<float>(p, jo, plane_out)[obase] = (float)r;
             if (p.out_mask) p.out_mask[jm * plane_out + obase] = m ? 1 : 0;
             ++jj;
         }
@@ -112,8 +122,8 @@ spectral_interp_kernel(const __grid_constant__ InterpParams p) {
         // nothing included in this spaxel: data NaN, mask False (spectral_cube.py:3311-3313); only
         // differs from what was emitted when a finite fill / fill_value was in play
         for (int64_t j = 0; j < p.nchan_out; ++j) {
-            if (OUT64) reinterpret_cast<double *>(p.out)[j * plane_out + obase] = nan64();
-            else       reinterpret_cast<float *>(p.out)[j * plane_out + obase] = nan32();
+            if (OUT64) interp_out_row<double>(p, j, plane_out)[obase] = nan64();
+            else       interp_out_row<float>(p, j, plane_out)[obase] = nan32();
             if (p.out_mask) p.out_mask[j * plane_out + obase] = 0;
         }
     }
@@ -250,11 +260,11 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
             const int64_t jm = (p.mode == 1) ? jj : jo;
             if (active) {
                 if (OUT64) {
-                    double *o = reinterpret_cast<double *>(p.out) + jo * plane_out + obase;
+                    double *o = interp_out_row<double>(p, jo, plane_out) + obase;
                     *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
                     *reinterpret_cast<double2 *>(o + 2) = make_double2(r[2], r[3]);
                 } else {
-                    float *o = reinterpret_cast<float *>(p.out) + jo * plane_out + obase;
+                    float *o = interp_out_row<float>(p, jo, plane_out) + obase;
                     *reinterpret_cast<float4 *>(o) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
                 }
                 if (p.out_mask) *reinterpret_cast<uint32_t *>(p.out_mask + jm * plane_out + obase) = mbits;
@@ -288,8 +298,8 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
         for (int k = 0; k < 4; ++k) {
             if (any_included[k]) continue;
             for (int64_t j = 0; j < p.nchan_out; ++j) {
-                if (OUT64) reinterpret_cast<double *>(p.out)[j * plane_out + obase + k] = nan64();
-                else       reinterpret_cast<float *>(p.out)[j * plane_out + obase + k] = nan32();
+                if (OUT64) interp_out_row<double>(p, j, plane_out)[obase + k] = nan64();
+                else       interp_out_row<float>(p, j, plane_out)[obase + k] = nan32();
                 if (p.out_mask) p.out_mask[j * plane_out + obase + k] = 0;
             }
         }
@@ -343,18 +353,19 @@ static cudaError_t launch_interp(const InterpParams &p, cudaStream_t s) {
 
 using namespace scb;
 
-extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uint8_t *out_mask,
-                                  int64_t nchan, int64_t ny, int64_t nx,
-                                  int64_t stride_c, int64_t stride_y,
-                                  int64_t nchan_out,
-                                  const sc_mask_desc *mask, double fill,
-                                  const double *in_axis, const double *grid,
-                                  int has_fill_value, double fill_value,
-                                  int in_reversed, int out_reversed, int mode,
-                                  void *workspace, size_t workspace_bytes, void *stream) {
+static int spectral_interp_impl(const float *in, void *out, int out_dtype, uint8_t *out_mask,
+                                int64_t nchan, int64_t ny, int64_t nx,
+                                int64_t stride_c, int64_t stride_y,
+                                int64_t nchan_out,
+                                const sc_mask_desc *mask, double fill,
+                                const double *in_axis, const double *grid,
+                                int has_fill_value, double fill_value,
+                                int in_reversed, int out_reversed, int mode,
+                                const uint64_t *out_chan_ptrs,
+                                void *workspace, size_t workspace_bytes, void *stream) {
     int rc = check_cube_args(in, nchan, ny, nx, stride_c, stride_y);
     if (rc) return rc;
-    SC_CHECK_ARG(out != nullptr, "out is NULL");
+    SC_CHECK_ARG(out != nullptr || out_chan_ptrs != nullptr, "out is NULL");
     SC_CHECK_ARG(out_dtype == SC_F32 || out_dtype == SC_F64, "out_dtype must be SC_F32 or SC_F64");
     SC_CHECK_ARG(nchan_out > 0 && nchan_out < ((int64_t)1 << 31) && nchan < ((int64_t)1 << 31), "bad channel counts");
     SC_CHECK_ARG(in_axis && grid, "in_axis / grid must not be NULL");
@@ -404,6 +415,7 @@ extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uin
     p.nchan = nchan; p.ny = ny; p.nx = nx; p.stride_c = stride_c; p.stride_y = stride_y; p.nchan_out = nchan_out;
     p.lut = lut_dev; p.fill = (float)fill; p.has_fill_value = has_fill_value; p.fill_value = fill_value;
     p.in_reversed = in_reversed; p.out_reversed = out_reversed; p.mode = mode;
+    p.out_chan_ptrs = out_chan_ptrs;
     rc = build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
     if (rc) return rc;
     LaunchScope ls(SC_OP_SPECTRAL_INTERP, s);
@@ -417,4 +429,33 @@ extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uin
         e = out_dtype == SC_F64 ? launch_interp<1>(p, s) : launch_interp<0>(p, s);
     if (e != cudaSuccess) return cuda_fail(e, "spectral_interp_kernel launch");
     return SC_OK;
+}
+
+extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uint8_t *out_mask,
+                                  int64_t nchan, int64_t ny, int64_t nx,
+                                  int64_t stride_c, int64_t stride_y,
+                                  int64_t nchan_out,
+                                  const sc_mask_desc *mask, double fill,
+                                  const double *in_axis, const double *grid,
+                                  int has_fill_value, double fill_value,
+                                  int in_reversed, int out_reversed, int mode,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    return spectral_interp_impl(in, out, out_dtype, out_mask, nchan, ny, nx, stride_c, stride_y, nchan_out, mask, fill,
+                                in_axis, grid, has_fill_value, fill_value, in_reversed, out_reversed, mode, nullptr,
+                                workspace, workspace_bytes, stream);
+}
+
+extern "C" int sc_spectral_interp_scatter(const float *in, const uint64_t *out_chan_ptrs, int out_dtype, uint8_t *out_mask,
+                                          int64_t nchan, int64_t ny, int64_t nx,
+                                          int64_t stride_c, int64_t stride_y,
+                                          int64_t nchan_out,
+                                          const sc_mask_desc *mask, double fill,
+                                          const double *in_axis, const double *grid,
+                                          int has_fill_value, double fill_value,
+                                          int in_reversed, int out_reversed, int mode,
+                                          void *workspace, size_t workspace_bytes, void *stream) {
+    SC_CHECK_ARG(out_chan_ptrs != nullptr, "out_chan_ptrs is NULL");
+    return spectral_interp_impl(in, nullptr, out_dtype, out_mask, nchan, ny, nx, stride_c, stride_y, nchan_out, mask, fill,
+                                in_axis, grid, has_fill_value, fill_value, in_reversed, out_reversed, mode, out_chan_ptrs,
+                                workspace, workspace_bytes, stream);
 }

@@ -765,12 +765,9 @@ class BaseSpectralCube(object):
         return cube
 
     # -- spectral resampling (spectral_cube.py:3224-3332; dask_spectral_cube.py:1250-1373) --------------
-    def spectral_interpolate(self, spectral_grid, suppress_smooth_warning=False, fill_value=None,
-                             update_function=None, force_rechunk=True, **kwargs):
-        """Resample the cube spectrally onto ``spectral_grid`` (values in the cube's spectral unit,
-        or a Quantity-like with ``.value``); linear interpolation per spaxel."""
-        torch = _torch()
-        lib = _lib.load()
+    def _interp_axes(self, spectral_grid, suppress_smooth_warning):
+        """The checks and flips of spectral_cube.py:3240-3290: (grid ascending, input axis ascending, reverse_in,
+        reverse_out, mean output spacing)."""
         grid = np.asarray(getattr(spectral_grid, 'value', spectral_grid), dtype=np.float64)
         inaxis = self.spectral_axis
         indiff = np.mean(np.diff(inaxis))
@@ -791,7 +788,30 @@ class BaseSpectralCube(object):
         if outdiff > 2 * indiff and not suppress_smooth_warning:
             warnings.warn("Input grid has too small a spacing. The data should "
                           "be smoothed prior to resampling.", SmoothingWarning)
+        return grid, inaxis, reverse_in, reverse_out, outdiff
 
+    def _interp_wcs(self, grid, reverse_out, outdiff):
+        """new spectral WCS: crpix=1, crval = first grid value as given, cdelt = +-mean spacing (:3317-3324)"""
+        newwcs = self._wcs.copy()
+        inv = 1.0 / self._spectral_scale
+        newwcs.crpix[2] = 1.0
+        newwcs.crval[2] = (grid[-1] if reverse_out else grid[0]) * inv
+        newwcs.cdelt[2] = (-outdiff if reverse_out else outdiff) * inv
+        newwcs.pc[2, :] = [0.0, 0.0, 1.0]
+        return newwcs
+
+    def _interp_nan_filled(self, fill_value):
+        """Is the interpolated data already NaN wherever its new mask excludes it?"""
+        return (fill_value is None or fill_value != fill_value) and \
+            (self._mirrors_dask or float(self._fill_value) != float(self._fill_value))
+
+    def spectral_interpolate(self, spectral_grid, suppress_smooth_warning=False, fill_value=None,
+                             update_function=None, force_rechunk=True, **kwargs):
+        """Resample the cube spectrally onto ``spectral_grid`` (values in the cube's spectral unit,
+        or a Quantity-like with ``.value``); linear interpolation per spaxel."""
+        torch = _torch()
+        lib = _lib.load()
+        grid, inaxis, reverse_in, reverse_out, outdiff = self._interp_axes(spectral_grid, suppress_smooth_warning)
         src = self._data
         nchan, ny, nx = self.shape
         nout = grid.size
@@ -808,13 +828,7 @@ class BaseSpectralCube(object):
             ip, gp, 0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
             1 if reverse_in else 0, 1 if reverse_out else 0, 1 if dask else 0,
             ws.data_ptr(), ws.numel(), _stream()))
-        # new spectral WCS: crpix=1, crval = first grid value as given, cdelt = +-mean spacing (:3317-3324)
-        newwcs = self._wcs.copy()
-        inv = 1.0 / self._spectral_scale
-        newwcs.crpix[2] = 1.0
-        newwcs.crval[2] = (grid[-1] if reverse_out else grid[0]) * inv
-        newwcs.cdelt[2] = (-outdiff if reverse_out else outdiff) * inv
-        newwcs.pc[2, :] = [0.0, 0.0, 1.0]
+        newwcs = self._interp_wcs(grid, reverse_out, outdiff)
         newmask = BooleanArrayMask(omask, wcs=newwcs)
         if dask:
             cube = self._new_cube_with(data=out.to(torch.float32), wcs=newwcs, mask=newmask)
@@ -822,8 +836,35 @@ class BaseSpectralCube(object):
         else:
             cube = self._new_cube_with(data=out, wcs=newwcs, mask=newmask)
         cube._mask = newmask
-        cube._nan_filled_already = (fill_value is None or fill_value != fill_value) and (dask or float(self._fill_value) != float(self._fill_value))
+        cube._nan_filled_already = self._interp_nan_filled(fill_value)
         return cube
+
+    def _spectral_interpolate_scatter(self, spectral_grid, chan_ptrs, suppress_smooth_warning=False, fill_value=None):
+        """`spectral_interpolate` of these rows with every output channel stored where ``chan_ptrs`` (device int64
+        tensor, one address per output channel IN OUTPUT ORDER) says -- the channel owners' buffers of a row-sharded job
+        (`distributed.RowShardedCube.spectral_interpolate_to_channels`).  float32 NaN-filled data only: what `reproject`
+        consumes.  Returns the new spectral WCS."""
+        torch = _torch()
+        lib = _lib.load()
+        if not self._interp_nan_filled(fill_value):
+            raise ValueError("the scattered form carries no mask: it needs a NaN fill value (the data must say what is masked)")
+        grid, inaxis, reverse_in, reverse_out, outdiff = self._interp_axes(spectral_grid, suppress_smooth_warning)
+        src = self._data
+        nchan, ny, nx = self.shape
+        nout = grid.size
+        if chan_ptrs.numel() != nout or chan_ptrs.dtype != torch.int64 or chan_ptrs.device != src.device:
+            raise ValueError("chan_ptrs: one int64 address per output channel, on the cube's device")
+        desc, keep = self._mask_desc()
+        ws = self._get_workspace(lib.sc_workspace_bytes(_lib.OP_SPECTRAL_INTERP, nchan, ny, nx, nout))
+        (ia, ip), (ga, gp) = _lib.as_double_array(inaxis), _lib.as_double_array(grid)
+        _lib.check(lib.sc_spectral_interp_scatter(
+            src.data_ptr(), chan_ptrs.data_ptr(), _lib.F32, None,
+            nchan, ny, nx, src.stride(0), src.stride(1), nout, desc,
+            float('nan') if self._mirrors_dask else float(self._fill_value),
+            ip, gp, 0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
+            1 if reverse_in else 0, 1 if reverse_out else 0, 1 if self._mirrors_dask else 0,
+            ws.data_ptr(), ws.numel(), _stream()))
+        return self._interp_wcs(grid, reverse_out, outdiff)
 
     # -- reprojection (spectral_cube.py:2649-2746) -------------------------------------------------------
     _ORDERS = {'nearest-neighbor': 0, 'bilinear': 1, 0: 0, 1: 1}

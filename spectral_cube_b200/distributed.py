@@ -100,6 +100,20 @@ def release_peer_buffers():
     _PEER['buffers'].clear()
 
 
+def _peer_available(device, group):
+    """Can this job map peer buffers (torch symmetric memory)?  Tried once; the reason it cannot is kept for the warning."""
+    if _PEER['broken'] is not None:
+        return False
+    try:
+        _peer_buffer((1, 1, 4), device, group)
+        return True
+    except Exception as exc:
+        import warnings
+        _PEER['broken'] = repr(exc)
+        warnings.warn("peer-memory buffers unavailable (%s); using NCCL" % (_PEER['broken'][:200],))
+        return False
+
+
 def _reshard_rows_to_channels_peer(local, ny_total, group, borrow):
     """One kernel per rank stores every channel of the local row block straight into its final place in the
     destination rank's buffer over NVLink peer memory (`sc_reshard_scatter`): no staging, no concatenation pass."""
@@ -281,6 +295,59 @@ class RowShardedCube(object):
     def spectral_interpolate(self, grid, **kw):
         return self._wrap(self.local.spectral_interpolate(grid, **kw))
 
+    def spectral_interpolate_to_channels(self, grid, mode='auto', **kw):
+        """``spectral_interpolate`` whose result is sharded over CHANNELS: (cube of this rank's output channels over
+        the whole image, (c0, c1)) -- what ``reproject`` needs next (``cube.spectral_interpolate(grid).reproject(hdr)``
+        on a row-sharded cube is config 5).  ``mode='peer'``: the interpolation kernel stores every output channel
+        straight into its owner's buffer over NVLink peer memory (`sc_spectral_interp_scatter`): its stores ARE the
+        re-shard, the row-sharded intermediate is never written.  ``mode='twostep'``: interpolate locally, then
+        ``reshard_rows_to_channels``.  ``'auto'`` takes the peer path when it is available.  The data arrive NaN-filled
+        where the interpolated mask excludes them (no mask travels), so a non-NaN fill value needs ``'twostep'``."""
+        import torch
+        dist = _dist()
+        loc = self.local
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        nout = int(np.asarray(getattr(grid, 'value', grid)).size)
+        nchan, rows, nx = loc.shape
+        if mode not in ('auto', 'peer', 'twostep'):
+            raise ValueError("mode must be 'auto', 'peer' or 'twostep'")
+        src = loc._data
+        peer_ok = (world > 1 and world <= 16 and src.is_cuda and nx % 4 == 0 and dist.get_backend(self.group) == 'nccl' and
+                   loc._interp_nan_filled(kw.get('fill_value')))
+        if mode == 'peer' and not peer_ok:
+            raise ValueError("the peer path needs an NCCL job of 2..16 CUDA ranks, nx % 4 == 0 and a NaN fill value")
+        cparts = channel_partition(nout, world)
+        c0, c1 = cparts[rank]
+        if mode == 'twostep' or not peer_ok or (mode == 'auto' and not _peer_available(src.device, self.group)):
+            reshard_mode = kw.pop('reshard_mode', 'auto')
+            rows_cube = loc.spectral_interpolate(grid, **kw)
+            chan_local = reshard_rows_to_channels(rows_cube._filled_tensor(rows_cube._fill_value), self.ny_total, self.group,
+                                                  mode=reshard_mode, borrow=True)
+            newwcs = rows_cube._wcs.copy()
+        else:
+            chans_max = max(b - a for a, b in cparts)
+            buf, hdl = _peer_buffer((chans_max, self.ny_total, nx), src.device, self.group)
+            # address of (channel j - c0(owner), row y0, column 0) in the owner's buffer, for every output channel j
+            plane = self.ny_total * nx * 4
+            ptrs = np.empty(nout, dtype=np.int64)
+            for d, (a, b) in enumerate(cparts):
+                ptrs[a:b] = int(hdl.buffer_ptrs[d]) + (np.arange(b - a, dtype=np.int64) * plane) + self.y0 * nx * 4
+            chan_ptrs = torch.from_numpy(ptrs).to(src.device)
+            from . import _lib
+            kw.pop('reshard_mode', None)
+            with _lib.on_device_of(src):
+                hdl.barrier()                                 # every rank is done with the buffer's previous contents
+                newwcs = loc._spectral_interpolate_scatter(grid, chan_ptrs, **kw)
+                hdl.barrier()                                 # every rank's stores have landed
+            chan_local = buf[:c1 - c0]
+        w = newwcs
+        w.crpix[1] += self.y0                                  # back to the full image's WCS
+        w.crpix[2] -= c0
+        sub = type(loc)(chan_local, w, unit=loc._unit, fill_value=loc._fill_value, spectral_unit=loc._spectral_unit,
+                        allow_huge_operations=loc.allow_huge_operations)
+        sub._nan_filled_already = True
+        return sub, (c0, c1)
+
     # ---- spatial_smooth / convolve_to: halo rows from the two neighbours ------------------------------------
     def _is_sharded(self):
         dist = _dist()
@@ -398,11 +465,24 @@ class RowShardedCube(object):
         w.crpix[2] -= c0
         sub = type(loc)(chan_local, w, unit=loc._unit, fill_value=loc._fill_value, spectral_unit=loc._spectral_unit,
                         allow_huge_operations=loc.allow_huge_operations)
+        return self._reproject_channel_shard(sub, c0, c1, header, order, **kw), (c0, c1)
+
+    @staticmethod
+    def _reproject_channel_shard(sub, c0, c1, header, order='bilinear', **kw):
+        """`reproject` of one rank's channels: the target header / WCS restricted to channels [c0, c1)."""
         if hasattr(header, 'celestial_params'):
             so = tuple(kw.pop('shape_out'))
             kw['shape_out'] = (c1 - c0,) + so[1:]
-            return sub.reproject(header, order=order, filled=False, **kw), (c0, c1)
+            return sub.reproject(header, order=order, filled=False, **kw)
         hdr = dict(header)
         hdr['NAXIS3'] = c1 - c0
         hdr['CRPIX3'] = hdr.get('CRPIX3', 1.0) - c0
-        return sub.reproject(hdr, order=order, filled=False, **kw), (c0, c1)
+        return sub.reproject(hdr, order=order, filled=False, **kw)
+
+    def spectral_interpolate_reproject(self, grid, header, order='bilinear', mode='auto', **kw):
+        """Config 5 on a row-sharded cube, ``cube.spectral_interpolate(grid).reproject(header)``: the interpolation
+        kernel scatters its output to the channel owners (``spectral_interpolate_to_channels``), every rank reprojects
+        its channels.  Returns (cube of this rank's channels over the output image, (c0, c1))."""
+        interp_kw = {k: kw.pop(k) for k in ('suppress_smooth_warning', 'fill_value') if k in kw}
+        sub, (c0, c1) = self.spectral_interpolate_to_channels(grid, mode=mode, **interp_kw)
+        return self._reproject_channel_shard(sub, c0, c1, header, order, **kw), (c0, c1)

@@ -4,8 +4,8 @@ Sharded-versus-whole parity on the GPUs of one job (no oracle involved: both sid
 ``sharded_parity()`` runs inside an initialised ``torch.distributed`` NCCL job, one rank per GPU.  Every
 rank regenerates the same small synthetic cube, processes its own row block through ``RowShardedCube``
 and compares with the single-GPU result on the whole cube: moments (no exchange), ``spatial_smooth``
-(halo rows from the neighbours, both exchange modes), ``convolve_to`` and ``reproject`` (rows -> channels
-all-to-all).  Results must be bit-identical.  Used by ``tests/test_multigpu_gpu.py`` and by
+(halo rows from the neighbours, both exchange modes), ``convolve_to``, ``reproject`` (rows -> channels
+re-shard) and the interpolate -> reproject job whose interpolation kernel scatters to the channel owners.  Results must be bit-identical.  Used by ``tests/test_multigpu_gpu.py`` and by
 ``bench.py --gpus N`` (N >= 2), so that the sharded path has evidence wherever a multi-GPU job runs.
 """
 import warnings
@@ -83,6 +83,24 @@ def sharded_parity(group=None, rows_per_rank=48):
         ref = whole.reproject(hdr)._data_hi
         sub, (c0, c1) = shard.reproject(hdr)
         res['reproject'] = same(sub._data_hi, ref[c0:c1], 'reproject')
+        # config 5 as one sharded job: the interpolation kernel scatters its output to the channel owners (peer memory when
+        # the platform has it), then every rank reprojects its channels -- against the same two calls on the whole cube
+        grid = whole.spectral_axis[::2]
+        ref_i = whole.spectral_interpolate(grid)
+        ci0, ci1 = D.channel_partition(len(grid), world)[rank]
+        for mode in ('twostep', 'peer'):
+            try:
+                sub, (a0, a1) = shard.spectral_interpolate_to_channels(grid, mode=mode)
+                res['interp_to_channels_' + mode] = (a0, a1) == (ci0, ci1) and same(sub._data, ref_i._data[ci0:ci1], 'interp_to_channels_' + mode)
+            except Exception as exc:
+                if mode == 'twostep':
+                    raise
+                detail['interp_to_channels_peer_unavailable'] = repr(exc)[:300]
+        hdr2 = dict(ref_i.header)
+        hdr2.update({'PC1_1': np.cos(a), 'PC1_2': -np.sin(a), 'PC2_1': np.sin(a), 'PC2_2': np.cos(a)})
+        ref = ref_i.reproject(hdr2)._data_hi
+        sub, (a0, a1) = shard.spectral_interpolate_reproject(grid, hdr2)
+        res['interp_reproject'] = same(sub._data_hi, ref[a0:a1], 'interp_reproject')
     res['_detail'] = detail
     return res
 

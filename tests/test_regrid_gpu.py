@@ -125,6 +125,38 @@ def test_spectral_interpolate_matches_oracle(gridname, fill_value, flip_in, kern
 
 
 @use_dask
+@pytest.mark.parametrize('kernel', ['direct', 'tma'])
+@pytest.mark.parametrize('reverse_out', [False, True])
+def test_scattered_interpolation_equals_the_plain_one(use_dask, reverse_out, kernel, monkeypatch):
+    """`sc_spectral_interp_scatter` (the form a row-sharded job uses to hand every output channel to its owner) with a
+    pointer table that scatters the channels over two separate buffers, in a shuffled order: bit-identical with
+    `spectral_interpolate` of the same cube."""
+    import torch
+    monkeypatch.setenv('SC_INTERP_KERNEL', '1' if kernel == 'direct' else '2')
+    data = _random_cube((24, 6, 16), seed=43, nan_frac=0.08)
+    sc = gpu_cube(data, BENCH_WCS, use_dask=use_dask, spectral_unit='km/s')
+    sa = np.sort(sc.spectral_axis)
+    grid = np.linspace(sa[1], sa[-2], 11)
+    if reverse_out:
+        grid = grid[::-1]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        want = sc.spectral_interpolate(grid)
+        ny, nx = data.shape[1:]
+        bufs = [torch.full((6, ny + 3, nx), -1.0, dtype=torch.float32, device='cuda') for _ in range(2)]   # rows 2 .. 2 + ny
+        where = [(j % 2, [3, 0, 5, 1, 4, 2][j // 2]) for j in range(11)]   # (buffer, channel slot) of output channel j
+        assert len(set(where)) == 11
+        ptrs = torch.tensor([bufs[b].data_ptr() + ((slot * (ny + 3) + 2) * nx) * 4 for b, slot in where],
+                            dtype=torch.int64, device='cuda')
+        sc._spectral_interpolate_scatter(grid, ptrs)
+    ref = want._data
+    for j, (b, slot) in enumerate(where):
+        got = bufs[b][slot, 2:2 + ny]
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref[j], nan=-7.0)), j
+        assert bool((bufs[b][slot, :2] == -1.0).all()) and bool((bufs[b][slot, 2 + ny:] == -1.0).all())   # nothing else touched
+
+
+@use_dask
 @pytest.mark.parametrize('reverse_out', [False, True])
 def test_interpolate_benchmark_block_matches_oracle(use_dask, reverse_out, monkeypatch):
     """Config 5's interpolation (2048 -> 1024 channels on 4096-wide rows) on an 8-row block of the benchmark cube,
