@@ -325,7 +325,10 @@ int sc_spectral_interp(const float *in, void *out, int out_dtype, uint8_t *out_m
  * and pointing at row `y0` of channel j in the buffer of the rank that owns that channel -- this rank's own buffer or a
  * peer's mapped over NVLink (torch symmetric memory `buffer_ptrs`).  The interpolation kernel's stores ARE the exchange:
  * no row-sharded result is written and read again, no all-to-all follows.  The caller brackets the call with a barrier
- * among the ranks on both sides.  `out_mask` (may be NULL) stays local, (nchan_out, ny, nx). */
+ * among the ranks on both sides.  `out_mask` (may be NULL) stays local, (nchan_out, ny, nx).
+ * `phase` / `nphases` (rank / world, nphases <= 16): CTA b starts its march over the spectrum at the fraction
+ * ((phase + b) % nphases) / nphases of it and wraps around, so that at any moment the ranks of a job store to all channel
+ * owners in equal shares instead of all to the same one; 0 / 1 = plain order. */
 int sc_spectral_interp_scatter(const float *in, const uint64_t *out_chan_ptrs, int out_dtype, uint8_t *out_mask,
                                int64_t nchan, int64_t ny, int64_t nx,
                                int64_t stride_c, int64_t stride_y,
@@ -334,6 +337,7 @@ int sc_spectral_interp_scatter(const float *in, const uint64_t *out_chan_ptrs, i
                                const double *in_axis, const double *grid,
                                int has_fill_value, double fill_value,
                                int in_reversed, int out_reversed, int mode,
+                               int phase, int nphases,
                                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- reprojection ----------------------------------------------------------------------

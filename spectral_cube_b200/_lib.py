@@ -97,7 +97,7 @@ SIGNATURES = {
     'sc_spectral_interp': (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
                                   _pd, _pd, _i32, _dbl, _i32, _i32, _i32, _vp, _sz, _vp]),
     'sc_spectral_interp_scatter': (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
-                                          _pd, _pd, _i32, _dbl, _i32, _i32, _i32, _vp, _sz, _vp]),
+                                          _pd, _pd, _i32, _dbl, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     'sc_reproject': (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,
                             _vp, _vp, _i32, _vp]),
     'sc_reproject_ex': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pmask, _dbl,

@@ -46,12 +46,24 @@ struct InterpParams {
     // out_chan_ptrs[j] + y * nx + x -- a pointer into the buffer of the rank that owns channel j, local or a peer's
     // over NVLink -- instead of out + (j * ny + y) * nx + x
     const uint64_t *out_chan_ptrs;
+    // scatter form, TMA kernel: a CTA's march over the spectrum starts at slab `slab_start[.][ph]` (slabs of 8 / of 4
+    // channels: first index 0 / 1) with LUT entry `jj_start[.][ph]`, runs to the end of the spectrum and then from channel 0
+    // up to the start again; ph = (phase + blockIdx.x) % nphases.  A job of N ranks passes phase = rank, nphases = N: at
+    // any moment the CTAs of every rank store to ALL channel owners in equal shares.  (All ranks marching 0 -> nchan
+    // together stored to the same owner at the same time: 425 GB/s per GPU; one phase per RANK: 559; per CTA: see DESIGN.)
+    int phase, nphases;
+    int slab_start[2][16], jj_start[2][16];
     DevMask mask;
 };
 
 template <typename T>
 __device__ __forceinline__ T *interp_out_row(const InterpParams &p, int64_t j, int64_t plane_out) {
     if (p.out_chan_ptrs) return reinterpret_cast<T *>(__ldg(p.out_chan_ptrs + j));
+    return reinterpret_cast<T *>(p.out) + j * plane_out;
+}
+template <typename T, bool SCATTER>
+__device__ __forceinline__ T *interp_out_row_t(const InterpParams &p, int64_t j, int64_t plane_out) {
+    if (SCATTER) return reinterpret_cast<T *>(__ldg(p.out_chan_ptrs + j));
     return reinterpret_cast<T *>(p.out) + j * plane_out;
 }
 
@@ -163,7 +175,7 @@ struct InterpSmem {
     uint64_t empty[IT_STAGES];
 };
 
-template <int MODE, int OUT64, int IT_CB, int IT_STAGES>
+template <int MODE, int OUT64, int IT_CB, int IT_STAGES, bool SCATTER>
 __global__ void __launch_bounds__(IT_THREADS, (IT_CB * IT_STAGES <= 20 ? 5 : 4))
 spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per_row) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -174,6 +186,11 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     const int64_t x0 = (tile - y * tiles_per_row) * IT_TILE;
     const int width = (int)min((int64_t)IT_TILE, p.nx - x0);
     const int n_iter = (int)((p.nchan + IT_CB - 1) / IT_CB);
+    // the march: slabs start .. n_iter - 1, then (scatter form with a phase) 0 .. start, the last one for its first channel only
+    // (the plain form is compiled without any of this: start = 0 folds the second leg and the phase table away)
+    const int ph = (SCATTER && p.nphases > 1) ? (int)((p.phase + blockIdx.x) % (unsigned)p.nphases) : 0;
+    const int start = SCATTER ? p.slab_start[IT_CB == 8 ? 0 : 1][ph] : 0;
+    const int n_first = n_iter - start, n_total = start > 0 ? n_iter + 1 : n_iter;
     if (tid == 0) {
         for (int s = 0; s < IT_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], IT_CONS / 32); }
         mbar_fence_init();
@@ -183,11 +200,12 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
         const float *src = p.in + y * p.stride_y + x0;
         const uint64_t pol = l2_evict_first_policy();
         const uint32_t row_bytes = (uint32_t)width * 4u;
-        for (int it = 0; it < n_iter; ++it) {
-            const int s = it % IT_STAGES;
+        for (int q = 0; q < n_total; ++q) {
+            const int s = q % IT_STAGES;
+            const int it = q < n_first ? start + q : q - n_first;
             const int64_t i0 = (int64_t)it * IT_CB;
-            const int nch = (int)min((int64_t)IT_CB, p.nchan - i0);
-            if (it >= IT_STAGES) mbar_wait(&sm.empty[s], ((it / IT_STAGES) - 1) & 1);
+            const int nch = (start > 0 && q == n_total - 1) ? 1 : (int)min((int64_t)IT_CB, p.nchan - i0);
+            if (q >= IT_STAGES) mbar_wait(&sm.empty[s], ((q / IT_STAGES) - 1) & 1);
             if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)nch * row_bytes);
             __syncwarp();
             if (lane < nch) {
@@ -209,12 +227,19 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
     float va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
     uint32_t inc_a = 0u, inc_b = 0u;                     // include bits (bit k = spaxel k) of the samples in va / vb
     uint32_t any_inc = 0u;
-    int64_t jj = 0;
+    int64_t jj = SCATTER ? p.jj_start[IT_CB == 8 ? 0 : 1][ph] : 0;
     // LUT entries ride in registers, requested TWO (weights) and THREE ({need, kind}) outputs before they are used: one
     // ahead left 28 % of the warp samples waiting on that load when an output is due every second channel.  The weights
     // of even / odd outputs live in two register pairs that are reloaded in place (a copy would wait for the load).
-    double2 w_even = lut_weights(p.lut, 0, p.nchan_out), w_odd = lut_weights(p.lut, 1, p.nchan_out);
-    int2 nk0 = lut_need_kind(p.lut, 0, p.nchan_out), nk1 = lut_need_kind(p.lut, 1, p.nchan_out), nk2 = lut_need_kind(p.lut, 2, p.nchan_out);
+    double2 w_even, w_odd;
+    int2 nk0, nk1, nk2;
+    auto seek = [&](int64_t j) {                         // position the look-ahead registers on LUT entry j
+        jj = j;
+        w_even = lut_weights(p.lut, j + (j & 1), p.nchan_out);
+        w_odd = lut_weights(p.lut, j + 1 - (j & 1), p.nchan_out);
+        nk0 = lut_need_kind(p.lut, j, p.nchan_out); nk1 = lut_need_kind(p.lut, j + 1, p.nchan_out); nk2 = lut_need_kind(p.lut, j + 2, p.nchan_out);
+    };
+    seek(jj);
 
     auto take = [&](float (&dst)[4], uint32_t &inc, int s, int cb, int64_t ch) {
         const float4 v = *reinterpret_cast<const float4 *>(&sm.data[s][cb][xo]);
@@ -260,11 +285,11 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
             const int64_t jm = (p.mode == 1) ? jj : jo;
             if (active) {
                 if (OUT64) {
-                    double *o = interp_out_row<double>(p, jo, plane_out) + obase;
+                    double *o = interp_out_row_t<double, SCATTER>(p, jo, plane_out) + obase;
                     *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
                     *reinterpret_cast<double2 *>(o + 2) = make_double2(r[2], r[3]);
                 } else {
-                    float *o = interp_out_row<float>(p, jo, plane_out) + obase;
+                    float *o = interp_out_row_t<float, SCATTER>(p, jo, plane_out) + obase;
                     *reinterpret_cast<float4 *>(o) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
                 }
                 if (p.out_mask) *reinterpret_cast<uint32_t *>(p.out_mask + jm * plane_out + obase) = mbits;
@@ -273,11 +298,13 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
         }
     };
     static_assert(IT_CB % 2 == 0, "the register sets swap roles with the channel parity");
-    for (int it = 0; it < n_iter; ++it) {
-        const int s = it % IT_STAGES;
+    for (int q = 0; q < n_total; ++q) {
+        const int s = q % IT_STAGES;
+        const int it = q < n_first ? start + q : q - n_first;
         const int64_t i0 = (int64_t)it * IT_CB;
-        const int nch = (int)min((int64_t)IT_CB, p.nchan - i0);
-        mbar_wait(&sm.full[s], (it / IT_STAGES) & 1);
+        const int nch = (start > 0 && q == n_total - 1) ? 1 : (int)min((int64_t)IT_CB, p.nchan - i0);
+        if (start > 0 && q == n_first) seek(0);                          // second leg of the march: from channel 0 up to the start
+        mbar_wait(&sm.full[s], (q / IT_STAGES) & 1);
         for (int cb = 0; cb < nch; cb += 2) {
             const int64_t i = i0 + cb;                                   // even ascending-order channel: into va, vb is the previous one
             take(va, inc_a, s, cb, p.in_reversed ? p.nchan - 1 - i : i);
@@ -298,8 +325,8 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
         for (int k = 0; k < 4; ++k) {
             if (any_included[k]) continue;
             for (int64_t j = 0; j < p.nchan_out; ++j) {
-                if (OUT64) interp_out_row<double>(p, j, plane_out)[obase + k] = nan64();
-                else       interp_out_row<float>(p, j, plane_out)[obase + k] = nan32();
+                if (OUT64) interp_out_row_t<double, SCATTER>(p, j, plane_out)[obase + k] = nan64();
+                else       interp_out_row_t<float, SCATTER>(p, j, plane_out)[obase + k] = nan32();
                 if (p.out_mask) p.out_mask[j * plane_out + obase + k] = 0;
             }
         }
@@ -308,7 +335,14 @@ spectral_interp_tma_kernel(const __grid_constant__ InterpParams p, int tiles_per
 
 template <int MODE, int OUT64, int CB, int STAGES>
 static cudaError_t launch_interp_tma_ring(const InterpParams &p, unsigned grid, int tiles_per_row, cudaStream_t s) {
-    auto kern = spectral_interp_tma_kernel<MODE, OUT64, CB, STAGES>;
+    if (p.out_chan_ptrs) {
+        auto kern = spectral_interp_tma_kernel<MODE, OUT64, CB, STAGES, true>;
+        static unsigned long long configured = 0;    // per instantiation, one bit per device
+        if (cudaError_t e = ensure_dyn_smem(kern, sizeof(InterpSmem<CB, STAGES>), &configured)) return e;
+        kern<<<grid, IT_THREADS, sizeof(InterpSmem<CB, STAGES>), s>>>(p, tiles_per_row);
+        return cudaGetLastError();
+    }
+    auto kern = spectral_interp_tma_kernel<MODE, OUT64, CB, STAGES, false>;
     static unsigned long long configured = 0;        // per instantiation, one bit per device
     if (cudaError_t e = ensure_dyn_smem(kern, sizeof(InterpSmem<CB, STAGES>), &configured)) return e;
     kern<<<grid, IT_THREADS, sizeof(InterpSmem<CB, STAGES>), s>>>(p, tiles_per_row);
@@ -361,7 +395,7 @@ static int spectral_interp_impl(const float *in, void *out, int out_dtype, uint8
                                 const double *in_axis, const double *grid,
                                 int has_fill_value, double fill_value,
                                 int in_reversed, int out_reversed, int mode,
-                                const uint64_t *out_chan_ptrs,
+                                const uint64_t *out_chan_ptrs, int phase, int nphases,
                                 void *workspace, size_t workspace_bytes, void *stream) {
     int rc = check_cube_args(in, nchan, ny, nx, stride_c, stride_y);
     if (rc) return rc;
@@ -416,6 +450,20 @@ static int spectral_interp_impl(const float *in, void *out, int out_dtype, uint8
     p.lut = lut_dev; p.fill = (float)fill; p.has_fill_value = has_fill_value; p.fill_value = fill_value;
     p.in_reversed = in_reversed; p.out_reversed = out_reversed; p.mode = mode;
     p.out_chan_ptrs = out_chan_ptrs;
+    p.phase = phase; p.nphases = nphases;
+    for (int v = 0; v < 2; ++v) {
+        const int64_t cb = v == 0 ? 8 : 4, n_iter = cdiv(nchan, cb);
+        for (int ph = 0; ph < 16; ++ph) {
+            const int64_t start = (nphases > 1 && ph < nphases) ? n_iter * ph / nphases : 0;
+            // the first leg begins with a channel that serves only as the LOWER neighbour there: entries with
+            // need <= start * cb are emitted by the second leg, which ends on that very channel
+            int64_t j0 = 0;
+            if (start > 0)
+                j0 = std::upper_bound(lut.begin(), lut.end(), start * cb,
+                                      [](int64_t c, const InterpEntry &e) { return c < (int64_t)e.need; }) - lut.begin();
+            p.slab_start[v][ph] = (int)start; p.jj_start[v][ph] = (int)j0;
+        }
+    }
     rc = build_dev_mask(mask, in, stride_c, stride_y, &p.mask);
     if (rc) return rc;
     LaunchScope ls(SC_OP_SPECTRAL_INTERP, s);
@@ -441,7 +489,7 @@ extern "C" int sc_spectral_interp(const float *in, void *out, int out_dtype, uin
                                   int in_reversed, int out_reversed, int mode,
                                   void *workspace, size_t workspace_bytes, void *stream) {
     return spectral_interp_impl(in, out, out_dtype, out_mask, nchan, ny, nx, stride_c, stride_y, nchan_out, mask, fill,
-                                in_axis, grid, has_fill_value, fill_value, in_reversed, out_reversed, mode, nullptr,
+                                in_axis, grid, has_fill_value, fill_value, in_reversed, out_reversed, mode, nullptr, 0, 1,
                                 workspace, workspace_bytes, stream);
 }
 
@@ -453,9 +501,11 @@ extern "C" int sc_spectral_interp_scatter(const float *in, const uint64_t *out_c
                                           const double *in_axis, const double *grid,
                                           int has_fill_value, double fill_value,
                                           int in_reversed, int out_reversed, int mode,
+                                          int phase, int nphases,
                                           void *workspace, size_t workspace_bytes, void *stream) {
     SC_CHECK_ARG(out_chan_ptrs != nullptr, "out_chan_ptrs is NULL");
+    SC_CHECK_ARG(nphases >= 1 && nphases <= 16 && phase >= 0 && phase < nphases, "phase must be in [0, nphases), nphases <= 16");
     return spectral_interp_impl(in, nullptr, out_dtype, out_mask, nchan, ny, nx, stride_c, stride_y, nchan_out, mask, fill,
                                 in_axis, grid, has_fill_value, fill_value, in_reversed, out_reversed, mode, out_chan_ptrs,
-                                workspace, workspace_bytes, stream);
+                                phase, nphases, workspace, workspace_bytes, stream);
 }

@@ -839,11 +839,13 @@ class BaseSpectralCube(object):
         cube._nan_filled_already = self._interp_nan_filled(fill_value)
         return cube
 
-    def _spectral_interpolate_scatter(self, spectral_grid, chan_ptrs, suppress_smooth_warning=False, fill_value=None):
+    def _spectral_interpolate_scatter(self, spectral_grid, chan_ptrs, suppress_smooth_warning=False, fill_value=None,
+                                      phase=0, nphases=1):
         """`spectral_interpolate` of these rows with every output channel stored where ``chan_ptrs`` (device int64
         tensor, one address per output channel IN OUTPUT ORDER) says -- the channel owners' buffers of a row-sharded job
         (`distributed.RowShardedCube.spectral_interpolate_to_channels`).  float32 NaN-filled data only: what `reproject`
-        consumes.  Returns the new spectral WCS."""
+        consumes.  ``phase`` / ``nphases`` = rank / world: staggers the ranks' marches over the spectrum.  Returns the new
+        spectral WCS."""
         torch = _torch()
         lib = _lib.load()
         if not self._interp_nan_filled(fill_value):
@@ -863,7 +865,7 @@ class BaseSpectralCube(object):
             float('nan') if self._mirrors_dask else float(self._fill_value),
             ip, gp, 0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
             1 if reverse_in else 0, 1 if reverse_out else 0, 1 if self._mirrors_dask else 0,
-            ws.data_ptr(), ws.numel(), _stream()))
+            int(phase), int(nphases), ws.data_ptr(), ws.numel(), _stream()))
         return self._interp_wcs(grid, reverse_out, outdiff)
 
     # -- reprojection (spectral_cube.py:2649-2746) -------------------------------------------------------

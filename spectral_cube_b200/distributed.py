@@ -337,7 +337,7 @@ class RowShardedCube(object):
             kw.pop('reshard_mode', None)
             with _lib.on_device_of(src):
                 hdl.barrier()                                 # every rank is done with the buffer's previous contents
-                newwcs = loc._spectral_interpolate_scatter(grid, chan_ptrs, **kw)
+                newwcs = loc._spectral_interpolate_scatter(grid, chan_ptrs, phase=rank, nphases=world, **kw)
                 hdl.barrier()                                 # every rank's stores have landed
             chan_local = buf[:c1 - c0]
         w = newwcs

@@ -125,18 +125,20 @@ def test_spectral_interpolate_matches_oracle(gridname, fill_value, flip_in, kern
 
 
 @use_dask
+@pytest.mark.parametrize('phase', [(0, 1), (3, 8), (7, 8), (1, 2)])
 @pytest.mark.parametrize('kernel', ['direct', 'tma'])
 @pytest.mark.parametrize('reverse_out', [False, True])
-def test_scattered_interpolation_equals_the_plain_one(use_dask, reverse_out, kernel, monkeypatch):
+def test_scattered_interpolation_equals_the_plain_one(use_dask, reverse_out, kernel, phase, monkeypatch):
     """`sc_spectral_interp_scatter` (the form a row-sharded job uses to hand every output channel to its owner) with a
     pointer table that scatters the channels over two separate buffers, in a shuffled order: bit-identical with
-    `spectral_interpolate` of the same cube."""
+    `spectral_interpolate` of the same cube -- also when the march over the spectrum starts in the middle and wraps
+    around (`phase`: how the ranks of a job avoid storing to the same owner at the same time)."""
     import torch
     monkeypatch.setenv('SC_INTERP_KERNEL', '1' if kernel == 'direct' else '2')
-    data = _random_cube((24, 6, 16), seed=43, nan_frac=0.08)
+    data = _random_cube((44, 6, 16), seed=43, nan_frac=0.08)
     sc = gpu_cube(data, BENCH_WCS, use_dask=use_dask, spectral_unit='km/s')
     sa = np.sort(sc.spectral_axis)
-    grid = np.linspace(sa[1], sa[-2], 11)
+    grid = np.linspace(sa[0] - 2 * (sa[1] - sa[0]), sa[-1] + 2 * (sa[1] - sa[0]), 11)   # incl. samples left / right of the axis and on knots
     if reverse_out:
         grid = grid[::-1]
     with warnings.catch_warnings():
@@ -148,7 +150,7 @@ def test_scattered_interpolation_equals_the_plain_one(use_dask, reverse_out, ker
         assert len(set(where)) == 11
         ptrs = torch.tensor([bufs[b].data_ptr() + ((slot * (ny + 3) + 2) * nx) * 4 for b, slot in where],
                             dtype=torch.int64, device='cuda')
-        sc._spectral_interpolate_scatter(grid, ptrs)
+        sc._spectral_interpolate_scatter(grid, ptrs, phase=phase[0], nphases=phase[1])
     ref = want._data
     for j, (b, slot) in enumerate(where):
         got = bufs[b][slot, 2:2 + ny]
