@@ -1041,6 +1041,27 @@ sep_fixup_kernel(const __grid_constant__ SpatialParams p) {
     }
 }
 
+// Which of the two exact treatments an output with almost nothing valid gets must not depend on how the image is cut into
+// blocks or shards (the two round differently in the last bit): it is decided per output, from its own window -- is one of
+// the two outermost window rows at least half populated?  Then the weight sits on well-populated rows (a horizontal edge
+// of a blank region) and the float64 re-fold is exact; otherwise (vertical edges, corners) the fix-up kernel redoes it.
+// (The column warps pace the pipeline: along a vertical edge two lanes of every block come here, and running the whole
+// re-fold for them cost 8 ms per shard; these two shared-memory reads do not.)
+template <int H>
+__device__ __forceinline__ bool pipe_outer_row_populated(const SpatialParams &p, const uint32_t *rdf, int b, int wrow0, int j0,
+                                                         int m0, int m1, int m2, int ccol) {
+    bool full_row = false;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int rel = j0 + (e ? 2 * H : 0) + wrow0, tb = rel >> 4;
+        const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
+        if (mt == PM_BLANK) continue;
+        const uint32_t d = mt == PM_CLEAN ? 0u : rdf[(((b - 2 + tb) % PP_NB) * PP_R + (rel & 15)) * SP_TX + ccol];
+        full_row |= d < (p.qsx >> 1);
+    }
+    return full_row;
+}
+
 // An output whose integer `present` is below fix_thresh: the kernel-row factors are folded again in float64 over the row
 // presences (qsx - rowdef) / qsx.  That is exact whenever the rows that carry the weight are themselves well populated -- the
 // horizontal edge of a blank region: full rows, reached only by the outermost kernel rows -- and the output is finished
@@ -1049,21 +1070,7 @@ sep_fixup_kernel(const __grid_constant__ SpatialParams p) {
 template <int H>
 __device__ __noinline__ double pipe_present_f64(const SpatialParams &p, const uint32_t *rdf, int b, int wrow0, int j0,
                                                 int m0, int m1, int m2, int ccol, bool *ok) {
-    // (the column warps pace the pipeline: along a VERTICAL edge two lanes of every block come here, and a full fold for each
-    // of them cost 8 ms per shard.  One look at the outermost rows of the window tells the two cases apart.)
     *ok = false;
-    {
-        bool full_row = false;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int rel = j0 + (e ? 2 * H : 0) + wrow0, tb = rel >> 4;
-            const int mt = tb == 0 ? m0 : tb == 1 ? m1 : m2;
-            if (mt == PM_BLANK) continue;
-            const uint32_t d = mt == PM_CLEAN ? 0u : rdf[(((b - 2 + tb) % PP_NB) * PP_R + (rel & 15)) * SP_TX + ccol];
-            full_row |= d < (p.qsx >> 1);
-        }
-        if (!full_row) return 0.0;
-    }
     double P = 0.0, E = 0.0;
     const double inv_qsx = 1.0 / (double)p.qsx;
     const uint32_t tiny = p.qsx >> 11;
@@ -1434,7 +1441,8 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                             bool ok = false;
                             double pf = 1.0;
                             const bool low = present != 0ull && present < p.fix_thresh && !pass;
-                            if (low) pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
+                            if (low && pipe_outer_row_populated<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol))
+                                pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
                             if (low && ok) res = a / pf;
                             else if (low) { res = __longlong_as_double((long long)PP_SENTINEL64); flagged = true; }
                             else if (hi < (1u << 24) || pass) res = sparse_rare_output(p, a, present, pass, c, yout + j0, x);
@@ -1502,13 +1510,6 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                         for (int j = 0; j < J; ++j) { fa[j] = (float)acc[j]; dd[j] = def[j]; }
                         const float *ip = p.in + c * p.stride_c + yout * p.stride_y + x;
                         float *o = reinterpret_cast<float *>(op);
-                        // outputs with almost nothing valid: along a HORIZONTAL edge most lanes of the warp hold some and the
-                        // float64 re-fold (all lanes busy) settles them here; along a vertical edge it is two lanes, which go
-                        // straight to the fix-up kernel (any answer of this vote is correct, it only picks the cheaper way)
-                        bool lowany = false;
-#pragma unroll
-                        for (int j = 0; j < J; ++j) lowany |= dd[j] != p.qall && p.qall - dd[j] < p.fix_thresh;
-                        const bool wide = __popc(__ballot_sync(__activemask(), lowany)) >= 8;
 #pragma unroll 1
                         while (rare) {
                             const int j0 = __ffs((int)rare) - 1;
@@ -1521,7 +1522,8 @@ sep_pipe_kernel(const __grid_constant__ SpatialParams p) {
                             } else if (present < p.fix_thresh) {
                                 bool ok = false;
                                 double pf = 1.0;
-                                if (wide) pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
+                                if (pipe_outer_row_populated<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol))
+                                    pf = pipe_present_f64<H>(p, rdf, b, wrow0, j0, m0, m1, m2, ccol, &ok);
                                 if (ok) r = (float)((double)fa[j0] / pf);
                                 else { r = __uint_as_float(PP_SENTINEL32); flagged = true; }   // redone exactly by sep_fixup_kernel
                             } else {
@@ -2035,7 +2037,8 @@ extern "C" int sc_spatial_smooth_sep_ex(const float *in, void *out, int out_dtyp
             p.fix_state = (unsigned int *)((uint8_t *)workspace + fix_off);
             p.fix_list = (uint32_t *)((uint8_t *)workspace + fix_off + 256);
             p.fix_bitmap = (uint32_t *)((uint8_t *)workspace + fix_off + 256 + (size_t)PP_FIX_CAP * 16);
-            p.fix_cap = PP_FIX_CAP;
+            // (SC_SPATIAL_FIX_CAP shrinks the list so that a test can reach the list-full path: the fix-up then scans every tile)
+            p.fix_cap = (uint32_t)std::min<long long>(PP_FIX_CAP, std::max(1, env_int("SC_SPATIAL_FIX_CAP", (int)PP_FIX_CAP)));
         }
         LaunchScope ls(SC_OP_SPATIAL_SMOOTH, s);
         cudaError_t e = cudaSuccess;

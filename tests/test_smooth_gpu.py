@@ -264,6 +264,60 @@ def test_spatial_smooth_benchmark_block_matches_oracle(kernel, use_dask, monkeyp
     assert_maps_close(got, want, rtol=RTOL, what='config-4 block, %s' % kernel)
 
 
+def test_spatial_smooth_fixup_list_full_scans_every_tile(monkeypatch):
+    """The pipe kernel lists the tiles that hold outputs to be redone exactly; when the list is full the fix-up kernel
+    scans the whole output instead.  A two-entry list forces that path: same result as with the full-size list."""
+    import torch
+    _force_kernel(monkeypatch, 'pipe_j8')
+    scb = _kernels()
+    from spectral_cube_b200.synth import synth_cube
+    dev = synth_cube(2, 72, 4096, y0=60, ny_total=4096, nx_total=4096, nan_permille=1, border=102)
+    k = scb.Gaussian2DKernel(8 / 2.3548200450309493)
+    ref = gpu_cube(dev, BENCH_WCS, use_dask=True).spatial_smooth(k)._data
+    monkeypatch.setenv('SC_SPATIAL_FIX_CAP', '2')
+    got = gpu_cube(dev, BENCH_WCS, use_dask=True).spatial_smooth(k)._data
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    assert not bool((got.view(torch.int32) == 0x7FC5CB20).any())          # no marker left behind
+
+
+def test_spatial_smooth_row_shards_across_a_blank_frame_equal_the_whole_image(monkeypatch):
+    """The exact treatment of blank-region edges (re-fold in the column warps, fix-up kernel) with halo rows: two row
+    shards of a block of the benchmark cube, cut INSIDE the rows where the blank frame ends, against the unsharded
+    result -- bit for bit -- and against the oracle."""
+    import torch
+    from spectral_cube_b200 import _lib
+    _force_kernel(monkeypatch, 'pipe_j8')
+    scb = _kernels()
+    lib = _lib.load()
+    from spectral_cube_b200.synth import synth_cube
+    from oracle.synth import synth_block
+    ny, nx, y0, cut = 96, 4096, 60, 40                       # frame ends at local row 42: its edge outputs straddle the cut
+    dev = synth_cube(1, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    k = scb.Gaussian2DKernel(8 / 2.3548200450309493)
+    h = k.shape[0] // 2
+    whole = gpu_cube(dev, BENCH_WCS, use_dask=True)
+    ref = whole.spatial_smooth(k)._data
+    top, bot = gpu_cube(dev[:, :cut].contiguous(), BENCH_WCS, use_dask=True), gpu_cube(dev[:, cut:].contiguous(), BENCH_WCS, use_dask=True)
+
+    def pack(cube, row0, nrows):
+        out = torch.empty((cube.shape[0], nrows, cube.shape[2]), dtype=torch.float32, device='cuda')
+        desc, keep = cube._mask_desc()
+        d = cube._data
+        _lib.check(lib.sc_pack_filled_rows(d.data_ptr(), d.shape[0], d.shape[1], d.shape[2], d.stride(0), d.stride(1),
+                                           desc, float('nan'), row0, nrows, out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        return out
+    halo_for_top, halo_for_bot = pack(bot, 0, h), pack(top, cut - h, h)
+    counts = top._spatial_strategy_counts() + bot._spatial_strategy_counts()
+    a = top._run_spatial_smooth(k.array, _lib.F32, halo_top=None, halo_bot=halo_for_top, halo_rows=h, strategy_counts=counts)
+    b = bot._run_spatial_smooth(k.array, _lib.F32, halo_top=halo_for_bot, halo_bot=None, halo_rows=h, strategy_counts=counts)
+    got = torch.cat([a, b], dim=1)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    host = synth_block(1, ny, nx, y0=y0, ny_total=4096, nx_total=nx, nan_permille=1, border=102)
+    want = oracle_cube(host, BENCH_WCS, use_dask=True).spatial_smooth(oconv.Gaussian2DKernel(8 / 2.3548200450309493))._data
+    assert_maps_close(got.cpu().numpy(), want, rtol=RTOL, what='two shards across the frame edge')
+
+
 def test_spatial_smooth_elliptical_and_nonseparable_match_oracle():
     scb = _kernels()
     data = _random_cube((2, 40, 64), seed=77, nan_frac=0.02)
