@@ -100,6 +100,19 @@ def release_peer_buffers():
     _PEER['buffers'].clear()
 
 
+def channel_row_pointers(buffer_ptrs, cparts, ny_total, nx, y0, itemsize=4):
+    """For every channel j of a cube that is being handed from row shards to channel shards: the address of
+    (channel j - c0(owner), row y0, column 0) in the OWNER's (chans, ny_total, nx) buffer -- ``buffer_ptrs[d]`` is rank d's
+    buffer as mapped into this process, ``cparts[d] = (c0, c1)`` the channels rank d owns.  int64 array of c1(last) entries:
+    the table `sc_spectral_interp_scatter` takes."""
+    nout = cparts[-1][1]
+    plane = int(ny_total) * int(nx) * itemsize
+    ptrs = np.empty(nout, dtype=np.int64)
+    for d, (a, b) in enumerate(cparts):
+        ptrs[a:b] = int(buffer_ptrs[d]) + np.arange(b - a, dtype=np.int64) * plane + int(y0) * int(nx) * itemsize
+    return ptrs
+
+
 def _peer_available(device, group):
     """Can this job map peer buffers (torch symmetric memory)?  Tried once; the reason it cannot is kept for the warning."""
     if _PEER['broken'] is not None:
@@ -327,12 +340,7 @@ class RowShardedCube(object):
         else:
             chans_max = max(b - a for a, b in cparts)
             buf, hdl = _peer_buffer((chans_max, self.ny_total, nx), src.device, self.group)
-            # address of (channel j - c0(owner), row y0, column 0) in the owner's buffer, for every output channel j
-            plane = self.ny_total * nx * 4
-            ptrs = np.empty(nout, dtype=np.int64)
-            for d, (a, b) in enumerate(cparts):
-                ptrs[a:b] = int(hdl.buffer_ptrs[d]) + (np.arange(b - a, dtype=np.int64) * plane) + self.y0 * nx * 4
-            chan_ptrs = torch.from_numpy(ptrs).to(src.device)
+            chan_ptrs = torch.from_numpy(channel_row_pointers(hdl.buffer_ptrs, cparts, self.ny_total, nx, self.y0)).to(src.device)
             from . import _lib
             kw.pop('reshard_mode', None)
             with _lib.on_device_of(src):

@@ -181,3 +181,28 @@ def _sharded_smoothing_job(rank, world):
 @pytest.mark.parametrize('world', [2, 3])
 def test_row_sharded_smoothing_host_logic(world):
     assert all(run_group(world, _sharded_smoothing_job))
+
+
+def test_channel_row_pointers_address_the_owners_rows():
+    """The table the scattering interpolation kernel stores through: channel j of a rank's rows [y0, y0 + rows) lands
+    in its owner's buffer at (j - c0, y0, 0); checked by writing through the table into numpy buffers."""
+    from spectral_cube_b200 import distributed as D
+    nout, ny_total, nx, world = 11, 12, 8, 3
+    cparts = D.channel_partition(nout, world)
+    chans_max = max(b - a for a, b in cparts)
+    bufs = [np.full((chans_max, ny_total, nx), -1.0, dtype=np.float32) for _ in range(world)]
+    base = [b.ctypes.data for b in bufs]
+    for rank, (y0, y1) in enumerate(D.row_partition(ny_total, world)):
+        ptrs = D.channel_row_pointers(base, cparts, ny_total, nx, y0)
+        assert ptrs.dtype == np.int64 and ptrs.shape == (nout,)
+        for j in range(nout):
+            owner = next(d for d, (a, b) in enumerate(cparts) if a <= j < b)
+            assert (int(ptrs[j]) - base[owner]) % 16 == 0                  # 16-byte vector stores need nx % 4 == 0 rows
+            off = (int(ptrs[j]) - base[owner]) // 4
+            assert 0 <= off and off + (y1 - y0) * nx <= bufs[owner].size
+            rows = bufs[owner].reshape(-1)[off:off + (y1 - y0) * nx].reshape(y1 - y0, nx)
+            rows[:] = 100 * j + np.arange(y0, y1)[:, None]                 # what a kernel storing through the table would do
+    for d, (a, b) in enumerate(cparts):
+        want = 100 * np.arange(a, b)[:, None, None] + np.arange(ny_total)[None, :, None] + np.zeros((1, 1, nx))
+        np.testing.assert_array_equal(bufs[d][:b - a], want.astype(np.float32))
+        assert np.all(bufs[d][b - a:] == -1.0)
