@@ -173,6 +173,43 @@ class Projection(LowerDimensionalObject):
         return Projection(out[0].cpu().numpy().astype(np.float64), unit=self._unit, wcs=self._wcs, meta=meta,
                           header=header, copy=False)
 
+    def reproject(self, header, order='bilinear'):
+        """Reproject the image into a new header (lower_dimensional_structures.py:496-538: `reproject_interp((value,
+        header), WCS(header), shape_out=..., order=order)`): the map goes to the device as a one-channel cube and through
+        `sc_wcs_pixel_map` + `sc_reproject_ex`, the kernels of `SpectralCube.reproject`.  NaN pixels poison the samples
+        they touch, pixels beyond half a pixel outside the image come out NaN; the result is float64 and carries the new
+        celestial WCS and the given header."""
+        from . import _lib
+        from .cube import BaseSpectralCube
+        from .wcs import CelestialWCS, CubeWCS
+        if not isinstance(self._wcs, CelestialWCS):
+            raise ValueError("WCS does not contain two spatial axes.")          # utils.WCSCelestialError
+        if order not in BaseSpectralCube._ORDERS:
+            raise NotImplementedError("order=%r: only 'nearest-neighbor' and 'bilinear' are implemented" % (order,))
+        hdr = dict(header)
+        ny_out, nx_out = int(hdr['NAXIS2']), int(hdr['NAXIS1'])
+
+        def lifted(ctype, crval, crpix, cdelt, pc, lonpole):
+            pc3 = np.eye(3)
+            pc3[:2, :2] = np.asarray(pc, dtype=np.float64)
+            return CubeWCS(list(ctype) + ['VRAD'], list(crval) + [0.0], list(crpix) + [1.0], list(cdelt) + [1.0],
+                           cunit=('deg', 'deg', 'm/s'), pc=pc3, lonpole=lonpole)
+        w = self._wcs
+        lift_hdr = dict(hdr)
+        lift_hdr.update({'CTYPE3': 'VRAD', 'CRVAL3': 0.0, 'CRPIX3': 1.0, 'CDELT3': 1.0, 'CUNIT3': 'm/s'})
+        for k in [k for k in lift_hdr if k.startswith(('PC3_', 'PC1_3', 'PC2_3', 'CD3_', 'CD1_3', 'CD2_3'))]:
+            del lift_hdr[k]
+        if any(k.startswith('CD') and k[2:3].isdigit() for k in lift_hdr):
+            lift_hdr['CD3_3'] = 1.0
+        target = CubeWCS.from_header(lift_hdr)
+        image = np.empty((1,) + self.shape, dtype=np.float32)             # a fresh block: proper strides for the size-1 axis
+        image[0] = self.value
+        plane = BaseSpectralCube(image, lifted(w.ctype, w.crval, w.crpix, w.cdelt, w.pc, w.lonpole))
+        yin, xin = plane._pixel_map(target, ny_out, nx_out)
+        out, _, _, _ = plane._run_reproject(yin, xin, BaseSpectralCube._ORDERS[order], filled=False)
+        return Projection(out[0].cpu().numpy(), unit=self._unit, wcs=target.celestial(), meta=self._meta,
+                          header=hdr, copy=False)
+
     def __new__(cls, value, unit=None, wcs=None, meta=None, header=None, copy=True):
         if np.ndim(value) != 2:  # noqa
             raise ValueError("value should be a 2-d array")

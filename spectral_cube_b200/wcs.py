@@ -235,6 +235,11 @@ class CelestialWCS(object):
             hdr['CRPIX%d' % n] = float(self.crpix[i])
             hdr['CDELT%d' % n] = float(self.cdelt[i])
             hdr['CUNIT%d' % n] = 'deg'
+            for j in range(2):
+                if float(np.asarray(self.pc)[i, j]) != (1.0 if i == j else 0.0):
+                    hdr['PC%d_%d' % (n, j + 1)] = float(np.asarray(self.pc)[i, j])
+        if self.lonpole is not None:
+            hdr['LONPOLE'] = float(self.lonpole)
         return hdr
 
 
